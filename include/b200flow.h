@@ -1,0 +1,210 @@
+/*
+ * b200flow.h -- C ABI of libb200flow.so, the B200-native (sm_100a) dense optical-flow engine.
+ *
+ * This is the drop-in boundary for the cv::cuda::DenseOpticalFlow family of
+ * opencv_contrib/modules/cudaoptflow.  Every entry point names the reference
+ * interface it replaces (paths relative to /root/reference/modules/cudaoptflow).
+ * Plain C: pointers + sizes only, no C++/torch types, no exceptions across the
+ * boundary; every function returns a b2f_status.
+ *
+ * Images are described the way cv::cuda::GpuMat describes them
+ * (opencv core cuda.hpp: data, step in BYTES, rows, cols, type flag), so the
+ * C++ adapter (include/b200flow/cudaoptflow_compat.hpp) is a field-for-field copy.
+ */
+#ifndef B200FLOW_H_
+#define B200FLOW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B2F_API
+#else
+#define B2F_API __attribute__((visibility("default")))
+#endif
+
+/* ---- status codes (reference: CV_Assert -> cv::Exception(StsAssert), cudaSafeCall ->
+ *      cv::Exception(GpuApiCallError); include/b200flow/cudaoptflow_compat.hpp maps back) ---- */
+typedef enum b2f_status {
+    B2F_OK = 0,
+    B2F_BAD_ARG = 1,          /* null pointer / invalid parameter value  (CV_Assert)          */
+    B2F_UNSUPPORTED_TYPE = 2, /* image type not accepted by this algorithm (CV_Assert on type) */
+    B2F_SIZE_MISMATCH = 3,    /* I0/I1/flow sizes differ                   (CV_Assert on size) */
+    B2F_CUDA_ERROR = 4,       /* a CUDA runtime call failed; see b2f_last_cuda_error()          */
+    B2F_NO_DEVICE = 5,        /* no usable sm_100 device                   (throw_no_cuda)      */
+    B2F_OUT_OF_MEMORY = 6
+} b2f_status;
+
+/* ---- image type flags: numerically equal to OpenCV's CV_MAKETYPE values ---- */
+enum {
+    B2F_8UC1 = 0,   /* CV_8UC1  */
+    B2F_32FC1 = 5,  /* CV_32FC1 */
+    B2F_32FC2 = 13  /* CV_32FC2 */
+};
+
+/* Mirror of the GpuMat fields that cross the boundary (data/step/rows/cols/type). `data` is a
+ * DEVICE pointer for b2f_calc and a HOST pointer for b2f_calc_host.  Rows may be pitched
+ * (step >= cols*elemSize), i.e. ROIs of larger GpuMats are accepted. */
+typedef struct b2f_image {
+    void *data;
+    size_t step; /* bytes */
+    int rows;
+    int cols;
+    int type;
+} b2f_image;
+
+/* ---- parameter blocks; field order and defaults mirror the reference's create() ---- */
+
+/* cv::cuda::OpticalFlowDual_TVL1::create  (include/opencv2/cudaoptflow.hpp:375-385) */
+typedef struct b2f_tvl1_params {
+    double tau;           /* 0.25 */
+    double lambda;        /* 0.15 */
+    double theta;         /* 0.3  */
+    int nscales;          /* 5    */
+    int warps;            /* 5    */
+    double epsilon;       /* 0.01 */
+    int iterations;       /* 300  */
+    double scale_step;    /* 0.8  */
+    double gamma;         /* 0.0  */
+    int use_initial_flow; /* 0    */
+} b2f_tvl1_params;
+
+/* cv::cuda::FarnebackOpticalFlow::create  (cudaoptflow.hpp:285-293) */
+typedef struct b2f_farneback_params {
+    int num_levels;    /* 5   */
+    double pyr_scale;  /* 0.5 */
+    int fast_pyramids; /* 0   */
+    int win_size;      /* 13  */
+    int num_iters;     /* 10  */
+    int poly_n;        /* 5   */
+    double poly_sigma; /* 1.1 */
+    int flags;         /* 0; B2F_OPTFLOW_* below */
+} b2f_farneback_params;
+
+enum {
+    B2F_OPTFLOW_USE_INITIAL_FLOW = 4,    /* cv::OPTFLOW_USE_INITIAL_FLOW   */
+    B2F_OPTFLOW_FARNEBACK_GAUSSIAN = 256 /* cv::OPTFLOW_FARNEBACK_GAUSSIAN */
+};
+
+/* cv::cuda::BroxOpticalFlow::create  (cudaoptflow.hpp:179-185) */
+typedef struct b2f_brox_params {
+    double alpha;          /* 0.197 flow smoothness              */
+    double gamma;          /* 50.0  gradient constancy importance */
+    double scale_factor;   /* 0.8   */
+    int inner_iterations;  /* 5     */
+    int outer_iterations;  /* 150   (cap on pyramid levels)       */
+    int solver_iterations; /* 10    */
+} b2f_brox_params;
+
+/* cv::cuda::DensePyrLKOpticalFlow::create  (cudaoptflow.hpp:245-249) */
+typedef struct b2f_denselk_params {
+    int win_width;        /* 13 */
+    int win_height;       /* 13 */
+    int max_level;        /* 3  */
+    int iters;            /* 30 */
+    int use_initial_flow; /* 0  */
+} b2f_denselk_params;
+
+typedef struct b2f_handle b2f_handle;
+
+/* ---- construction: replaces the static ::create() factories.  A NULL params pointer means
+ *      "the reference's defaults".  Parameter validation happens in b2f_calc, exactly where the
+ *      reference's CV_Asserts sit (src/tvl1flow.cpp:187-191, src/farneback.cpp:173-174,316-317,
+ *      src/brox.cpp:134-135, src/pyrlk.cpp:240-243). ---- */
+B2F_API void b2f_tvl1_default_params(b2f_tvl1_params *p);
+B2F_API void b2f_farneback_default_params(b2f_farneback_params *p);
+B2F_API void b2f_brox_default_params(b2f_brox_params *p);
+B2F_API void b2f_denselk_default_params(b2f_denselk_params *p);
+
+B2F_API int b2f_tvl1_create(const b2f_tvl1_params *p, b2f_handle **out);           /* src/tvl1flow.cpp:385-391 */
+B2F_API int b2f_farneback_create(const b2f_farneback_params *p, b2f_handle **out); /* src/farneback.cpp:484-489 */
+B2F_API int b2f_brox_create(const b2f_brox_params *p, b2f_handle **out);           /* src/brox.cpp:190-194 */
+B2F_API int b2f_denselk_create(const b2f_denselk_params *p, b2f_handle **out);     /* src/pyrlk.cpp:402-405 */
+B2F_API void b2f_destroy(b2f_handle *h);
+
+/* ---- getters/setters: replace getTau()/setTau() ... (cudaoptflow.hpp:158-177,233-243,261-283,
+ *      311-373).  Ids are per-algorithm; bools and ints travel as doubles. ---- */
+typedef enum b2f_param_id {
+    /* TV-L1 */
+    B2F_TVL1_TAU = 100, B2F_TVL1_LAMBDA, B2F_TVL1_THETA, B2F_TVL1_NSCALES, B2F_TVL1_WARPS,
+    B2F_TVL1_EPSILON, B2F_TVL1_ITERATIONS, B2F_TVL1_SCALE_STEP, B2F_TVL1_GAMMA,
+    B2F_TVL1_USE_INITIAL_FLOW,
+    /* Farneback */
+    B2F_FARN_NUM_LEVELS = 200, B2F_FARN_PYR_SCALE, B2F_FARN_FAST_PYRAMIDS, B2F_FARN_WIN_SIZE,
+    B2F_FARN_NUM_ITERS, B2F_FARN_POLY_N, B2F_FARN_POLY_SIGMA, B2F_FARN_FLAGS,
+    /* Brox */
+    B2F_BROX_ALPHA = 300, B2F_BROX_GAMMA, B2F_BROX_SCALE_FACTOR, B2F_BROX_INNER_ITERATIONS,
+    B2F_BROX_OUTER_ITERATIONS, B2F_BROX_SOLVER_ITERATIONS,
+    /* DensePyrLK */
+    B2F_LK_WIN_WIDTH = 400, B2F_LK_WIN_HEIGHT, B2F_LK_MAX_LEVEL, B2F_LK_ITERS,
+    B2F_LK_USE_INITIAL_FLOW,
+    /* engine knobs (no reference counterpart) */
+    B2F_ENGINE_FUSED_ITERS = 900, /* TV-L1: inner iterations fused per HBM pass (0 = auto)     */
+    B2F_ENGINE_USE_GRAPH = 901,   /* capture the fixed schedule in a CUDA graph (default 1)    */
+    B2F_ENGINE_KERNEL_PATH = 902  /* 0 = auto, 1 = unfused reference-shaped kernels (debug)    */
+} b2f_param_id;
+
+B2F_API int b2f_set_param(b2f_handle *h, int id, double value);
+B2F_API int b2f_get_param(const b2f_handle *h, int id, double *value);
+
+/* cv::Algorithm::getDefaultName(): "DenseOpticalFlow.OpticalFlowDual_TVL1" etc.
+ * (src/tvl1flow.cpp:122, src/farneback.cpp:132, src/brox.cpp:67, src/pyrlk.cpp:394). */
+B2F_API const char *b2f_default_name(const b2f_handle *h);
+
+/* ---- the hot call: replaces DenseOpticalFlow::calc(I0, I1, flow, stream)
+ *      (cudaoptflow.hpp:80; impls src/tvl1flow.cpp:170, src/farneback.cpp:167, src/brox.cpp:129,
+ *      src/pyrlk.cpp:379).
+ *   I0, I1 : device images, equal size/type.  TV-L1: 8UC1 (0..255) or 32FC1 (0..1, scaled x255);
+ *            Farneback: 8UC1 or 32FC1 (no scaling); Brox: 32FC1 in [0,1]; DensePyrLK: 8UC1.
+ *   flow   : device image, 32FC2, same size, allocated by the caller (the C++ adapter does the
+ *            GpuMat::create the reference does inside calc).  Read first only when the
+ *            algorithm's use-initial-flow option is set.
+ *   stream : a cudaStream_t (as void*).  All work is ordered after the caller's prior work on
+ *            that stream and is complete in stream order on return; no host synchronisation
+ *            happens inside the call unless stream == NULL (legacy default stream: the call
+ *            ends with a device synchronise, as the reference's launchers do). ---- */
+B2F_API int b2f_calc(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_image *flow,
+                     void *cuda_stream);
+
+/* Same contract with HOST buffers (pinned or pageable): uploads I0/I1, runs b2f_calc, downloads
+ * flow, all on `stream`; returns after the download has completed.  This is what a caller holding
+ * cv::Mat frames does with GpuMat::upload/download around calc (samples/optical_flow.cpp:170-238). */
+B2F_API int b2f_calc_host(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_image *flow,
+                          void *cuda_stream);
+
+/* Bytes of device workspace the handle holds (after the first calc) or would allocate for a
+ * rows x cols input of `type` (replaces brox.cpp:112-122 getBufSize / BufferPool sizing). */
+B2F_API size_t b2f_workspace_bytes(b2f_handle *h, int rows, int cols, int type);
+
+/* ---- diagnostics ---- */
+B2F_API const char *b2f_status_string(int status);
+B2F_API int b2f_last_cuda_error(const b2f_handle *h); /* cudaError_t of the last failure */
+B2F_API const char *b2f_version(void);
+
+/* Kernel launch accounting for bench.py ("gpu_launches") and the roofline line.  Classes are
+ * per algorithm; class 0 is always the dominant inner-loop kernel. */
+#define B2F_MAX_KERNEL_CLASSES 16
+typedef struct b2f_stats {
+    uint64_t calls;                                /* b2f_calc invocations                        */
+    uint64_t launches;                             /* kernel launches issued (graph nodes count)  */
+    uint64_t class_launches[B2F_MAX_KERNEL_CLASSES];
+    double class_ms[B2F_MAX_KERNEL_CLASSES];       /* CUDA-event time, only while profiling is on */
+    double class_bytes[B2F_MAX_KERNEL_CLASSES];    /* algorithmic bytes moved by those launches   */
+    int levels;                                    /* pyramid levels used by the last calc        */
+    int iterations_run;                            /* inner iterations executed by the last calc  */
+} b2f_stats;
+B2F_API int b2f_get_stats(b2f_handle *h, b2f_stats *out); /* synchronises the profiling events */
+B2F_API int b2f_reset_stats(b2f_handle *h);
+B2F_API const char *b2f_kernel_class_name(const b2f_handle *h, int cls);
+/* When on, every kernel launch is bracketed by CUDA events on the launching stream (graphs are
+ * bypassed) so per-class device time can be read back with b2f_get_stats. */
+B2F_API int b2f_set_profiling(b2f_handle *h, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FLOW_H_ */

@@ -1,0 +1,180 @@
+// common.cuh -- shared host/device plumbing for libb200flow (sm_100a only).
+//
+// Engine conventions:
+//  * every work plane is float32, row-major, pitch (in floats) a multiple of 32 so rows start on
+//    128-byte lines and are float4-loadable / TMA-addressable;
+//  * one arena (single cudaMalloc) per handle, laid out once per (rows, cols, params);
+//  * all kernels run on the caller's stream; no global mutable device state (__constant__
+//    symbols) so handles never interfere (the reference's global tables -- farneback.cu:60-63,
+//    pyrlk.cu:60-64 -- make concurrent instances race).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <float.h>
+#include <vector>
+#include <string>
+
+#include "b200flow.h"
+
+namespace b2f {
+
+// ---------------------------------------------------------------------------------------------
+// Plane views
+// ---------------------------------------------------------------------------------------------
+struct Plane {
+    float *p;
+    int pitch;  // floats
+    __host__ __device__ __forceinline__ float &at(int y, int x) const { return p[(size_t)y * pitch + x]; }
+    __host__ __device__ __forceinline__ float *row(int y) const { return p + (size_t)y * pitch; }
+};
+
+// Caller-provided image (possibly an ROI with arbitrary byte pitch).
+struct ImageView {
+    void *data;
+    size_t step;  // bytes
+    int rows, cols, type;
+};
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+static inline int plane_pitch(int cols) { return round_up(cols, 32); }
+
+// cvRound / saturate_cast<int>(double): round half to even.
+int cv_round(double v);
+
+// ---------------------------------------------------------------------------------------------
+// Arena: bump allocator over one device allocation
+// ---------------------------------------------------------------------------------------------
+class Arena {
+public:
+    ~Arena();
+    // Two-phase use: begin(true) + alloc... = counting pass; reserve(); begin(false) + alloc... again.
+    void begin(bool counting) { counting_ = counting; off_ = 0; }
+    Plane plane(int rows, int cols);
+    void *bytes(size_t n);
+    size_t used() const { return off_; }
+    size_t capacity() const { return cap_; }
+    cudaError_t reserve(size_t n);  // (re)allocates when n > capacity
+    void release();
+
+private:
+    char *base_ = nullptr;
+    size_t cap_ = 0, off_ = 0;
+    bool counting_ = true;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Launch context: stream + accounting + optional per-launch event timing
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+    cudaStream_t stream = nullptr;
+    b2f_stats *stats = nullptr;
+    bool profiling = false;
+    bool capturing = false;  // inside stream capture: no events, no error polling that syncs
+    cudaError_t err = cudaSuccess;
+    struct Timed { int cls; cudaEvent_t e0, e1; };
+    std::vector<Timed> *timed = nullptr;      // filled while profiling
+    std::vector<cudaEvent_t> *event_pool = nullptr;
+
+    void pre(int cls, double bytes);
+    void post(int cls);
+    bool ok() const { return err == cudaSuccess; }
+    void check(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
+};
+
+#define B2F_LAUNCH(ctx, cls, bytes, kernel, grid, block, smem, ...)                    \
+    do {                                                                                \
+        if ((ctx).ok()) {                                                               \
+            (ctx).pre((cls), (bytes));                                                  \
+            kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);             \
+            (ctx).post((cls));                                                          \
+        }                                                                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Handle base
+// ---------------------------------------------------------------------------------------------
+enum Algo { ALGO_TVL1 = 1, ALGO_FARNEBACK = 2, ALGO_BROX = 3, ALGO_DENSELK = 4 };
+
+struct EngineKnobs {
+    int fused_iters = 0;  // 0 = auto
+    int use_graph = 1;
+    int kernel_path = 0;  // 0 auto, 1 unfused reference-shaped kernels
+};
+
+}  // namespace b2f
+
+struct b2f_handle {
+    int algo = 0;
+    int last_cuda_error = 0;
+    b2f_stats stats{};
+    bool profiling = false;
+    b2f::EngineKnobs knobs;
+    b2f::Arena arena;
+    std::vector<b2f::Ctx::Timed> timed;
+    std::vector<cudaEvent_t> event_pool;
+    // staging for b2f_calc_host
+    void *host_stage = nullptr;
+    size_t host_stage_bytes = 0;
+
+    virtual ~b2f_handle();
+    virtual int calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, cudaStream_t s) = 0;
+    virtual int set_param(int id, double v) = 0;
+    virtual int get_param(int id, double *v) const = 0;
+    virtual const char *default_name() const = 0;
+    virtual const char *class_name(int cls) const = 0;
+    virtual size_t workspace_bytes(int rows, int cols, int type) = 0;
+
+    b2f::Ctx make_ctx(cudaStream_t s);
+    int finish(b2f::Ctx &ctx, cudaStream_t s);  // maps ctx.err -> status, NULL-stream sync
+    void collect_profile();
+};
+
+namespace b2f {
+
+// ---------------------------------------------------------------------------------------------
+// Shared kernels (pyramid.cu)
+// ---------------------------------------------------------------------------------------------
+// u8 / f32 image (arbitrary byte pitch) -> f32 plane * scale, two frames per launch.
+void convert_pair(Ctx &c, int cls, const ImageView &a, const ImageView &b, Plane da, Plane db, float scale);
+// cv::cuda::resize INTER_LINEAR semantics (top-left aligned; cudawarping/src/cuda/resize.cu:234-269),
+// two planes per launch, result multiplied by `mul` (fuses cuda::multiply, tvl1flow.cpp:299-300).
+void resize_linear_pair(Ctx &c, int cls, Plane sa, Plane sb, int srows, int scols, Plane da, Plane db,
+                        int drows, int dcols, float inv_fx, float inv_fy, float mul);
+void resize_linear_one(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, int drows, int dcols,
+                       float inv_fx, float inv_fy, float mul);
+// planar (u, v) -> interleaved CV_32FC2 (cudaarithm split_merge.cu:99-148) and back (:239).
+void merge_flow(Ctx &c, int cls, Plane u, Plane v, const ImageView &flow);
+void split_flow(Ctx &c, int cls, const ImageView &flow, Plane u, Plane v);
+void fill_plane(Ctx &c, Plane p, int rows, int cols, float value_bits_zero_only);
+// cv::cuda::pyrDown f32 C1 (cudawarping/src/cuda/pyr_down.cu:55-173): 5x5 [1 4 6 4 1]/16, REFLECT101.
+void pyr_down(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, int drows, int dcols);
+
+// resize.cpp:76-84 scale rule: scale passed to the kernel is float(1/f).
+static inline float inv_scale_from_sizes(int src, int dst) { return static_cast<float>(1.0 / (static_cast<double>(dst) / src)); }
+
+// ---------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+#endif
+
+}  // namespace b2f

@@ -1,0 +1,665 @@
+// tvl1.cu -- cv::cuda::OpticalFlowDual_TVL1 re-implemented for sm_100a.
+//
+// Reference being replaced (paths relative to /root/reference/modules/cudaoptflow):
+//   host  src/tvl1flow.cpp:170-382   (calc / calcImpl / procOneScale)
+//   dev   src/cuda/tvl1flow.cu:59-348 (centeredGradient, warpBackward, estimateU, estimateDualVariables)
+// plus cv::cuda::resize / multiply / merge / calcSum from cudawarping / cudaarithm.
+//
+// Kernel classes (b2f_stats.class_*):
+//   0 iter     inner primal-dual iteration(s)            64 B / px / iteration algorithmic
+//   1 warp     centred gradient + bicubic warp + rho/grad 32 B / px / warp
+//   2 pyramid  convert + bilinear pyramid                 ~8 B / dst px
+//   3 prolong  flow up-sampling (+rescale), split/merge
+//   4 reduce   deterministic error reduction (epsilon > 0 only)
+#include "common.cuh"
+#include "tvl1_math.cuh"
+#include "tvl1_blocked.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace b2f {
+
+namespace {
+
+enum { CLS_ITER = 0, CLS_WARP = 1, CLS_PYR = 2, CLS_PROLONG = 3, CLS_REDUCE = 4 };
+
+struct Tvl1Planes {
+    Plane I1wx, I1wy, grad, rho_c;
+    Plane u1, u2, u3;
+    Plane p11, p12, p21, p22, p31, p32;
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp: fuses centeredGradientKernel + warpBackwardKernel (tvl1flow.cu:59-164).
+// The gradients of I1 are formed on the fly from a 6x6 window of I1 (same 0.5f*(a-b) arithmetic
+// as the reference's separate gradient pass, so I1x/I1y never touch HBM); taps use clamp
+// addressing exactly like the reference's point/clamp textures; I1w is not stored (dead).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
+                                                   Plane grad, Plane rho, int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+
+    const float u1 = u1p.at(y, x);
+    const float u2 = u2p.at(y, x);
+    const float wx = x + u1;
+    const float wy = y + u2;
+    const float fx = floorf(wx), fy = floorf(wy);
+    // integer tap origin, kept in a range where int conversion is safe even for wild flows
+    const int ix = static_cast<int>(fminf(fmaxf(fx, -8.f), cols + 8.f)) - 1;
+    const int iy = static_cast<int>(fminf(fmaxf(fy, -8.f), rows + 8.f)) - 1;
+
+    float kx[4], ky[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        kx[i] = bicubic_coeff(wx - (fx + (i - 1)));
+        ky[i] = bicubic_coeff(wy - (fy + (i - 1)));
+    }
+
+    float sum = 0.f, sumx = 0.f, sumy = 0.f, wsum = 0.f;
+
+    if (ix >= 1 && iy >= 1 && ix + 4 <= cols - 1 && iy + 4 <= rows - 1) {
+        // interior: 6x6 window, no clamping
+        float win[6][6];
+        const float *base = &I1.at(iy - 1, ix - 1);
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) win[j][i] = __ldg(base + (size_t)j * I1.pitch + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float w = kx[i] * ky[j];
+                const float v = win[j + 1][i + 1];
+                const float gx = 0.5f * (win[j + 1][i + 2] - win[j + 1][i]);
+                const float gy = 0.5f * (win[j + 2][i + 1] - win[j][i + 1]);
+                sum = __fmaf_rn(w, v, sum);
+                sumx = __fmaf_rn(w, gx, sumx);
+                sumy = __fmaf_rn(w, gy, sumy);
+                wsum += w;
+            }
+        }
+    } else {
+        // border: clamp every tap, then take the clamped-neighbour gradient at the clamped tap
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cy = clampi(iy + j, 0, rows - 1);
+            const int cyp = min(cy + 1, rows - 1), cym = max(cy - 1, 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cx = clampi(ix + i, 0, cols - 1);
+                const int cxp = min(cx + 1, cols - 1), cxm = max(cx - 1, 0);
+                const float w = kx[i] * ky[j];
+                const float v = __ldg(&I1.at(cy, cx));
+                const float gx = 0.5f * (__ldg(&I1.at(cy, cxp)) - __ldg(&I1.at(cy, cxm)));
+                const float gy = 0.5f * (__ldg(&I1.at(cyp, cx)) - __ldg(&I1.at(cym, cx)));
+                sum = __fmaf_rn(w, v, sum);
+                sumx = __fmaf_rn(w, gx, sumx);
+                sumy = __fmaf_rn(w, gy, sumy);
+                wsum += w;
+            }
+        }
+    }
+
+    const float coeff = 1.0f / wsum;
+    const float I1w = sum * coeff;
+    const float Ix = sumx * coeff;
+    const float Iy = sumy * coeff;
+    I1wx.at(y, x) = Ix;
+    I1wy.at(y, x) = Iy;
+    grad.at(y, x) = __fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix));
+    const float I0v = I0.at(y, x);
+    rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unfused, reference-shaped inner iteration (any gamma, optional error image reduction).
+// Used for gamma != 0, for the epsilon > 0 cadence and as the cross-check for the blocked kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tvl1_estimate_u(Tvl1Planes P, int rows, int cols, Tvl1Scalars k,
+                                                         int calc_error, double *__restrict__ partials) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    float err = 0.f;
+    if (x < cols && y < rows) {
+        const float Ix = P.I1wx.at(y, x), Iy = P.I1wy.at(y, x);
+        const float g = P.grad.at(y, x), rc = P.rho_c.at(y, x);
+        const float u1 = P.u1.at(y, x), u2 = P.u2.at(y, x);
+        const float p11 = P.p11.at(y, x), p12 = P.p12.at(y, x);
+        const float p21 = P.p21.at(y, x), p22 = P.p22.at(y, x);
+        const float p11l = x > 0 ? P.p11.at(y, x - 1) : 0.f;
+        const float p21l = x > 0 ? P.p21.at(y, x - 1) : 0.f;
+        const float p12u = y > 0 ? P.p12.at(y - 1, x) : 0.f;
+        const float p22u = y > 0 ? P.p22.at(y - 1, x) : 0.f;
+        float u1n, u2n;
+        if (k.gamma == 0.f) {
+            tvl1_update_u(k, Ix, Iy, g, rc, u1, u2, p11, p11l, p12, p12u, p21, p21l, p22, p22u, u1n, u2n);
+        } else {
+            const float u3 = P.u3.at(y, x);
+            const float rho = __fadd_rn(rc, __fmaf_rn(k.gamma, u3, __fmaf_rn(Iy, u2, __fmul_rn(Ix, u1))));
+            const float fi = tvl1_threshold(rho, g, k.l_t);
+            const float v1 = __fmaf_rn(fi, Ix, u1);
+            const float v2 = __fmaf_rn(fi, Iy, u2);
+            const float v3 = __fmaf_rn(fi, k.gamma, u3);
+            const float p31 = P.p31.at(y, x), p32 = P.p32.at(y, x);
+            const float p31l = x > 0 ? P.p31.at(y, x - 1) : 0.f;
+            const float p32u = y > 0 ? P.p32.at(y - 1, x) : 0.f;
+            const float div1 = __fadd_rn(__fsub_rn(p11, p11l), __fsub_rn(p12, p12u));
+            const float div2 = __fadd_rn(__fsub_rn(p21, p21l), __fsub_rn(p22, p22u));
+            const float div3 = __fadd_rn(__fsub_rn(p31, p31l), __fsub_rn(p32, p32u));
+            u1n = __fmaf_rn(k.theta, div1, v1);
+            u2n = __fmaf_rn(k.theta, div2, v2);
+            P.u3.at(y, x) = __fmaf_rn(k.theta, div3, v3);
+        }
+        P.u1.at(y, x) = u1n;
+        P.u2.at(y, x) = u2n;
+        if (calc_error) {
+            const float d1 = u1 - u1n, d2 = u2 - u2n;  // u3 is not part of the GPU error (:284-286)
+            err = __fmaf_rn(d2, d2, __fmul_rn(d1, d1));
+        }
+    }
+    if (calc_error) {
+        // deterministic block reduction in double (the reference uses double atomics, sum.cu:107-133)
+        double v = static_cast<double>(err);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        __shared__ double wsum[8];
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        if ((tid & 31) == 0) wsum[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int i = 0; i < 8; ++i) s += wsum[i];
+            partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tvl1_estimate_dual(Tvl1Planes P, int rows, int cols, Tvl1Scalars k) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const int xr = min(x + 1, cols - 1), yd = min(y + 1, rows - 1);
+    {
+        const float c = P.u1.at(y, x);
+        const float ux = __fsub_rn(P.u1.at(y, xr), c), uy = __fsub_rn(P.u1.at(yd, x), c);
+        float pa = P.p11.at(y, x), pb = P.p12.at(y, x);
+        tvl1_update_p(k.taut, ux, uy, pa, pb);
+        P.p11.at(y, x) = pa;
+        P.p12.at(y, x) = pb;
+    }
+    {
+        const float c = P.u2.at(y, x);
+        const float ux = __fsub_rn(P.u2.at(y, xr), c), uy = __fsub_rn(P.u2.at(yd, x), c);
+        float pa = P.p21.at(y, x), pb = P.p22.at(y, x);
+        tvl1_update_p(k.taut, ux, uy, pa, pb);
+        P.p21.at(y, x) = pa;
+        P.p22.at(y, x) = pb;
+    }
+    if (k.gamma != 0.f) {
+        const float c = P.u3.at(y, x);
+        const float ux = __fsub_rn(P.u3.at(y, xr), c), uy = __fsub_rn(P.u3.at(yd, x), c);
+        float pa = P.p31.at(y, x), pb = P.p32.at(y, x);
+        tvl1_update_p(k.taut, ux, uy, pa, pb);
+        P.p31.at(y, x) = pa;
+        P.p32.at(y, x) = pb;
+    }
+}
+
+// Fixed-order final reduction of the per-block partial sums (single block).
+__global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, int n,
+                                                         double *__restrict__ out) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host engine
+// ---------------------------------------------------------------------------------------------
+struct Level {
+    int rows = 0, cols = 0;
+    Plane I0, I1, u1, u2;
+};
+
+class Tvl1Engine : public b2f_handle {
+public:
+    explicit Tvl1Engine(const b2f_tvl1_params &p) : P(p) { algo = ALGO_TVL1; }
+    ~Tvl1Engine() override {
+        if (err_host) cudaFreeHost(err_host);
+        destroy_graph();
+    }
+
+    b2f_tvl1_params P;
+
+    int calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, cudaStream_t s) override;
+    int set_param(int id, double v) override;
+    int get_param(int id, double *v) const override;
+    const char *default_name() const override { return "DenseOpticalFlow.OpticalFlowDual_TVL1"; }
+    const char *class_name(int cls) const override {
+        static const char *n[] = {"tvl1_iter", "tvl1_warp", "pyramid", "prolong_merge", "reduce"};
+        return (cls >= 0 && cls < 5) ? n[cls] : "";
+    }
+    size_t workspace_bytes(int rows, int cols, int type) override {
+        (void)type;
+        Layout L;
+        return layout(rows, cols, true, L);
+    }
+
+private:
+    struct Layout {
+        std::vector<Level> levels;  // all built levels (the last may be unused, <16 px rule)
+        int nscales = 0;            // levels actually solved
+        Plane u3[2];                // ping-pong full-res (gamma only)
+        float *shared[16] = {};     // level-shared planes, viewed with per-level pitch
+        double *partials = nullptr;
+        double *err_dev = nullptr;
+        int rows = 0, cols = 0;
+        bool gamma = false;
+        int nscales_param = 0;
+        double scale_step = 0;
+    };
+    Layout L_;
+    double *err_host = nullptr;
+
+    // graph cache (fixed schedule only)
+    cudaGraphExec_t graph_exec_ = nullptr;
+    struct GraphKey {
+        int rows = 0, cols = 0, type = -1;
+        b2f_tvl1_params P{};
+        EngineKnobs knobs;
+        void *base = nullptr;
+    } graph_key_;
+    uint64_t graph_launches_ = 0;
+    uint64_t graph_class_launches_[B2F_MAX_KERNEL_CLASSES] = {};
+    double graph_class_bytes_[B2F_MAX_KERNEL_CLASSES] = {};
+    int graph_iterations_ = 0;
+    void destroy_graph() {
+        if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        graph_exec_ = nullptr;
+    }
+
+    size_t layout(int rows, int cols, bool counting, Layout &L);
+    cudaError_t ensure_workspace(int rows, int cols);
+    Plane shared_plane(int idx, int cols) const { return Plane{L_.shared[idx], plane_pitch(cols)}; }
+    void solve(Ctx &c, bool allow_sync);
+    void proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync);
+};
+
+enum { SH_I1WX = 0, SH_I1WY, SH_GRAD, SH_RHO, SH_P11, SH_P12, SH_P21, SH_P22, SH_P31, SH_P32,
+       SH_U1B, SH_U2B, SH_P11B, SH_P12B, SH_P21B, SH_P22B, SH_COUNT };
+
+size_t Tvl1Engine::layout(int rows, int cols, bool counting, Layout &L) {
+    Arena tmp;
+    Arena &A = counting ? tmp : arena;
+    A.begin(counting);
+    L.levels.clear();
+    L.rows = rows;
+    L.cols = cols;
+    L.gamma = P.gamma != 0.0;
+    L.nscales_param = P.nscales;
+    L.scale_step = P.scale_step;
+    int r = rows, cc = cols;
+    int nscales = P.nscales;
+    for (int s = 0; s < P.nscales; ++s) {
+        if (s > 0) {
+            // cuda::resize dsize rule, resize.cpp:76-79
+            r = cv_round(r * P.scale_step);
+            cc = cv_round(cc * P.scale_step);
+            if (r < 1) r = 1;
+            if (cc < 1) cc = 1;
+        }
+        Level lv;
+        lv.rows = r;
+        lv.cols = cc;
+        lv.I0 = A.plane(r, cc);
+        lv.I1 = A.plane(r, cc);
+        lv.u1 = A.plane(r, cc);
+        lv.u2 = A.plane(r, cc);
+        L.levels.push_back(lv);
+        if (s > 0 && (cc < 16 || r < 16)) {  // tvl1flow.cpp:243-247
+            nscales = s;
+            break;
+        }
+    }
+    L.nscales = nscales;
+    for (int i = 0; i < SH_COUNT; ++i) {
+        if ((i == SH_P31 || i == SH_P32) && !L.gamma) {
+            L.shared[i] = nullptr;
+            continue;
+        }
+        L.shared[i] = A.plane(rows, cols).p;
+    }
+    if (L.gamma) {
+        L.u3[0] = A.plane(rows, cols);
+        L.u3[1] = A.plane(rows, cols);
+    }
+    const int nblocks = div_up(cols, 32) * div_up(rows, 8);
+    L.partials = static_cast<double *>(A.bytes(sizeof(double) * nblocks));
+    L.err_dev = static_cast<double *>(A.bytes(sizeof(double) * 4));
+    return A.used();
+}
+
+cudaError_t Tvl1Engine::ensure_workspace(int rows, int cols) {
+    const bool same = L_.rows == rows && L_.cols == cols && L_.gamma == (P.gamma != 0.0) &&
+                      L_.nscales_param == P.nscales && L_.scale_step == P.scale_step && arena.capacity() > 0;
+    if (same) return cudaSuccess;
+    Layout tmp;
+    const size_t need = layout(rows, cols, true, tmp);
+    destroy_graph();
+    cudaError_t e = arena.reserve(need);
+    if (e != cudaSuccess) return e;
+    layout(rows, cols, false, L_);
+    if (!err_host) e = cudaMallocHost(&err_host, sizeof(double) * 4);
+    return e;
+}
+
+void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
+    const Level &lv = L_.levels[s];
+    const int rows = lv.rows, cols = lv.cols;
+    const double npx = (double)rows * cols;
+    const double scaledEpsilon = P.epsilon * P.epsilon * npx;  // tvl1flow.cpp:310
+    const bool use_gamma = L_.gamma;
+
+    Tvl1Planes T;
+    T.I1wx = shared_plane(SH_I1WX, cols);
+    T.I1wy = shared_plane(SH_I1WY, cols);
+    T.grad = shared_plane(SH_GRAD, cols);
+    T.rho_c = shared_plane(SH_RHO, cols);
+    T.p11 = shared_plane(SH_P11, cols);
+    T.p12 = shared_plane(SH_P12, cols);
+    T.p21 = shared_plane(SH_P21, cols);
+    T.p22 = shared_plane(SH_P22, cols);
+    T.p31 = use_gamma ? shared_plane(SH_P31, cols) : Plane{nullptr, 0};
+    T.p32 = use_gamma ? shared_plane(SH_P32, cols) : Plane{nullptr, 0};
+    T.u1 = lv.u1;
+    T.u2 = lv.u2;
+    T.u3 = use_gamma ? Plane{u3cur.p, plane_pitch(cols)} : Plane{nullptr, 0};
+
+    // p = 0 (tvl1flow.cpp:338-346)
+    fill_plane(c, T.p11, rows, cols, 0.f);
+    fill_plane(c, T.p12, rows, cols, 0.f);
+    fill_plane(c, T.p21, rows, cols, 0.f);
+    fill_plane(c, T.p22, rows, cols, 0.f);
+    if (use_gamma) {
+        fill_plane(c, T.p31, rows, cols, 0.f);
+        fill_plane(c, T.p32, rows, cols, 0.f);
+    }
+
+    Tvl1Scalars k;
+    k.l_t = static_cast<float>(P.lambda * P.theta);  // tvl1flow.cpp:350-351
+    k.taut = static_cast<float>(P.tau / P.theta);
+    k.theta = static_cast<float>(P.theta);
+    k.gamma = static_cast<float>(P.gamma);
+
+    const dim3 block(32, 8);
+    const dim3 grid(div_up(cols, 32), div_up(rows, 8));
+    const int nblocks = grid.x * grid.y;
+
+    const bool fixed_schedule = !(P.epsilon > 0.0);
+    const bool blocked_ok = fixed_schedule && !use_gamma && knobs.kernel_path != 1;
+
+    Tvl1BlockedPlanes B;
+    if (blocked_ok) {
+        B.I1wx = T.I1wx; B.I1wy = T.I1wy; B.grad = T.grad; B.rho_c = T.rho_c;
+        B.s[0].u1 = T.u1; B.s[0].u2 = T.u2;
+        B.s[0].p11 = T.p11; B.s[0].p12 = T.p12; B.s[0].p21 = T.p21; B.s[0].p22 = T.p22;
+        B.s[1].u1 = shared_plane(SH_U1B, cols); B.s[1].u2 = shared_plane(SH_U2B, cols);
+        B.s[1].p11 = shared_plane(SH_P11B, cols); B.s[1].p12 = shared_plane(SH_P12B, cols);
+        B.s[1].p21 = shared_plane(SH_P21B, cols); B.s[1].p22 = shared_plane(SH_P22B, cols);
+    }
+    int cur = 0;  // which state set holds the current (u, p) in the blocked path
+
+    for (int w = 0; w < P.warps; ++w) {
+        const Plane wu1 = blocked_ok ? B.s[cur].u1 : T.u1;
+        const Plane wu2 = blocked_ok ? B.s[cur].u2 : T.u2;
+        B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, wu1, wu2, T.I1wx, T.I1wy,
+                   T.grad, T.rho_c, rows, cols);
+
+        if (blocked_ok) {
+            int done = 0;
+            while (done < P.iterations) {
+                const int kk = tvl1_blocked_pick_k(knobs.fused_iters, P.iterations - done, rows, cols);
+                tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);
+                cur ^= 1;
+                done += kk;
+            }
+            c.stats->iterations_run += P.iterations;
+            continue;
+        }
+
+        // reference cadence (tvl1flow.cpp:357-380)
+        double error = std::numeric_limits<double>::max();
+        double prevError = 0.0;
+        for (int n = 0; error > scaledEpsilon && n < P.iterations; ++n) {
+            const bool calcError = (P.epsilon > 0) && (n & 1) && (prevError < scaledEpsilon);
+            B2F_LAUNCH(c, CLS_ITER, 48.0 * npx, k_tvl1_estimate_u, grid, block, 0, T, rows, cols, k,
+                       calcError ? 1 : 0, L_.partials);
+            if (calcError) {
+                B2F_LAUNCH(c, CLS_REDUCE, 8.0 * nblocks, k_reduce_partials, dim3(1), dim3(256), 0, L_.partials,
+                           nblocks, L_.err_dev);
+                if (allow_sync && c.ok()) {
+                    c.check(cudaMemcpyAsync(err_host, L_.err_dev, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+                    c.check(cudaStreamSynchronize(c.stream));
+                    error = err_host[0];
+                    prevError = error;
+                }
+            } else {
+                error = std::numeric_limits<double>::max();
+                prevError -= scaledEpsilon;
+            }
+            B2F_LAUNCH(c, CLS_ITER, 40.0 * npx, k_tvl1_estimate_dual, grid, block, 0, T, rows, cols, k);
+            c.stats->iterations_run++;
+        }
+    }
+
+    if (blocked_ok && cur != 0) {
+        // the final (u1, u2) live in the B set; the level planes are the A set -> copy back
+        resize_linear_pair(c, CLS_PROLONG, B.s[1].u1, B.s[1].u2, rows, cols, lv.u1, lv.u2, rows, cols, 1.f, 1.f, 1.f);
+    }
+}
+
+void Tvl1Engine::solve(Ctx &c, bool allow_sync) {
+    const int ns = L_.nscales;
+    const bool use_gamma = L_.gamma;
+    int u3i = 0;
+    if (!P.use_initial_flow) {
+        fill_plane(c, L_.levels[ns - 1].u1, L_.levels[ns - 1].rows, L_.levels[ns - 1].cols, 0.f);
+        fill_plane(c, L_.levels[ns - 1].u2, L_.levels[ns - 1].rows, L_.levels[ns - 1].cols, 0.f);
+    }
+    if (use_gamma) fill_plane(c, L_.u3[0], L_.rows, L_.cols, 0.f);
+
+    for (int s = ns - 1; s >= 0; --s) {
+        proc_one_scale(c, s, L_.u3[u3i], allow_sync);
+        if (s == 0) break;
+        const Level &lo = L_.levels[s], &hi = L_.levels[s - 1];
+        const float inv_fx = inv_scale_from_sizes(lo.cols, hi.cols);
+        const float inv_fy = inv_scale_from_sizes(lo.rows, hi.rows);
+        const float mul = static_cast<float>(1.0 / P.scale_step);  // tvl1flow.cpp:299-300
+        resize_linear_pair(c, CLS_PROLONG, lo.u1, lo.u2, lo.rows, lo.cols, hi.u1, hi.u2, hi.rows, hi.cols, inv_fx,
+                           inv_fy, mul);
+        if (use_gamma) {  // resized, not rescaled (tvl1flow.cpp:293-296)
+            Plane src{L_.u3[u3i].p, plane_pitch(lo.cols)};
+            Plane dst{L_.u3[u3i ^ 1].p, plane_pitch(hi.cols)};
+            resize_linear_one(c, CLS_PROLONG, src, lo.rows, lo.cols, dst, hi.rows, hi.cols, inv_fx, inv_fy, 1.f);
+            u3i ^= 1;
+        }
+    }
+}
+
+int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, cudaStream_t s) {
+    // preconditions, tvl1flow.cpp:187-191
+    if (!(I0->type == B2F_8UC1 || I0->type == B2F_32FC1)) return B2F_UNSUPPORTED_TYPE;
+    if (I0->type != I1->type) return B2F_UNSUPPORTED_TYPE;
+    if (I0->rows != I1->rows || I0->cols != I1->cols) return B2F_SIZE_MISMATCH;
+    if (flow->type != B2F_32FC2) return B2F_UNSUPPORTED_TYPE;
+    if (flow->rows != I0->rows || flow->cols != I0->cols) return B2F_SIZE_MISMATCH;
+    if (P.nscales <= 0) return B2F_BAD_ARG;
+    if (P.warps < 0 || P.iterations < 0) return B2F_BAD_ARG;
+    if (P.nscales > 1 && !(P.scale_step > 0.0 && P.scale_step < 1.0)) return B2F_BAD_ARG;
+    if (!(P.theta > 0.0)) return B2F_BAD_ARG;
+    const size_t es = I0->type == B2F_8UC1 ? 1 : 4;
+    if (I0->step < I0->cols * es || I1->step < I1->cols * es || flow->step < (size_t)flow->cols * 8) return B2F_BAD_ARG;
+
+    const int rows = I0->rows, cols = I0->cols;
+    Ctx c = make_ctx(s);
+    c.check(tvl1_blocked_init());
+    c.check(ensure_workspace(rows, cols));
+    if (!c.ok()) return finish(c, s);
+    stats.levels = L_.nscales;
+    stats.iterations_run = 0;
+
+    const ImageView v0{I0->data, I0->step, rows, cols, I0->type};
+    const ImageView v1{I1->data, I1->step, rows, cols, I1->type};
+    const ImageView vf{flow->data, flow->step, rows, cols, B2F_32FC2};
+
+    // convertTo(CV_32F, 8U ? 1 : 255), tvl1flow.cpp:200-201
+    convert_pair(c, CLS_PYR, v0, v1, L_.levels[0].I0, L_.levels[0].I1, I0->type == B2F_8UC1 ? 1.0f : 255.0f);
+    if (P.use_initial_flow) split_flow(c, CLS_PROLONG, vf, L_.levels[0].u1, L_.levels[0].u2);
+
+    // image (and initial-flow) pyramid, tvl1flow.cpp:238-266
+    const int built = static_cast<int>(L_.levels.size());
+    for (int l = 1; l < built; ++l) {
+        const Level &a = L_.levels[l - 1], &b = L_.levels[l];
+        const float inv_f = static_cast<float>(1.0 / P.scale_step);  // fx given -> scale = float(1/fx)
+        resize_linear_pair(c, CLS_PYR, a.I0, a.I1, a.rows, a.cols, b.I0, b.I1, b.rows, b.cols, inv_f, inv_f, 1.f);
+        if (P.use_initial_flow && l < L_.nscales)
+            resize_linear_pair(c, CLS_PROLONG, a.u1, a.u2, a.rows, a.cols, b.u1, b.u2, b.rows, b.cols, inv_f, inv_f,
+                               static_cast<float>(P.scale_step));
+    }
+
+    const bool fixed_schedule = !(P.epsilon > 0.0);
+    const bool want_graph = knobs.use_graph && fixed_schedule && !profiling && s != nullptr;
+    if (want_graph) {
+        const bool hit = graph_exec_ && graph_key_.rows == rows && graph_key_.cols == cols &&
+                         std::memcmp(&graph_key_.P, &P, sizeof(P)) == 0 &&
+                         std::memcmp(&graph_key_.knobs, &knobs, sizeof(knobs)) == 0 &&
+                         graph_key_.base == L_.levels[0].I0.p;
+        if (!hit) {
+            destroy_graph();
+            cudaStream_t cs = nullptr;
+            c.check(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            if (c.ok()) {
+                Ctx g = make_ctx(cs);
+                b2f_stats scratch = stats;  // capture must not double-count launches
+                g.stats = &scratch;
+                g.capturing = true;
+                g.check(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+                if (g.ok()) solve(g, false);
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamEndCapture(cs, &graph);
+                g.check(e);
+                if (g.ok() && graph) g.check(cudaGraphInstantiate(&graph_exec_, graph, 0));
+                if (graph) cudaGraphDestroy(graph);
+                cudaStreamDestroy(cs);
+                graph_launches_ = scratch.launches - stats.launches;
+                for (int i = 0; i < B2F_MAX_KERNEL_CLASSES; ++i) {
+                    graph_class_launches_[i] = scratch.class_launches[i] - stats.class_launches[i];
+                    graph_class_bytes_[i] = scratch.class_bytes[i] - stats.class_bytes[i];
+                }
+                graph_iterations_ = scratch.iterations_run;
+                c.check(g.err);
+                if (c.ok()) {
+                    graph_key_.rows = rows;
+                    graph_key_.cols = cols;
+                    graph_key_.P = P;
+                    graph_key_.knobs = knobs;
+                    graph_key_.base = L_.levels[0].I0.p;
+                } else {
+                    destroy_graph();
+                }
+            }
+        }
+        if (c.ok() && graph_exec_) {
+            c.check(cudaGraphLaunch(graph_exec_, s));
+            stats.launches += graph_launches_;
+            for (int i = 0; i < B2F_MAX_KERNEL_CLASSES; ++i) {
+                stats.class_launches[i] += graph_class_launches_[i];
+                stats.class_bytes[i] += graph_class_bytes_[i];
+            }
+            stats.iterations_run = graph_iterations_;
+        }
+    } else {
+        solve(c, true);
+    }
+
+    // cuda::merge, tvl1flow.cpp:181-182
+    merge_flow(c, CLS_PROLONG, L_.levels[0].u1, L_.levels[0].u2, vf);
+    return finish(c, s);
+}
+
+int Tvl1Engine::set_param(int id, double v) {
+    switch (id) {
+        case B2F_TVL1_TAU: P.tau = v; break;
+        case B2F_TVL1_LAMBDA: P.lambda = v; break;
+        case B2F_TVL1_THETA: P.theta = v; break;
+        case B2F_TVL1_NSCALES: P.nscales = static_cast<int>(v); break;
+        case B2F_TVL1_WARPS: P.warps = static_cast<int>(v); break;
+        case B2F_TVL1_EPSILON: P.epsilon = v; break;
+        case B2F_TVL1_ITERATIONS: P.iterations = static_cast<int>(v); break;
+        case B2F_TVL1_SCALE_STEP: P.scale_step = v; break;
+        case B2F_TVL1_GAMMA: P.gamma = v; break;
+        case B2F_TVL1_USE_INITIAL_FLOW: P.use_initial_flow = v != 0; break;
+        default: return B2F_BAD_ARG;
+    }
+    return B2F_OK;
+}
+
+int Tvl1Engine::get_param(int id, double *v) const {
+    switch (id) {
+        case B2F_TVL1_TAU: *v = P.tau; break;
+        case B2F_TVL1_LAMBDA: *v = P.lambda; break;
+        case B2F_TVL1_THETA: *v = P.theta; break;
+        case B2F_TVL1_NSCALES: *v = P.nscales; break;
+        case B2F_TVL1_WARPS: *v = P.warps; break;
+        case B2F_TVL1_EPSILON: *v = P.epsilon; break;
+        case B2F_TVL1_ITERATIONS: *v = P.iterations; break;
+        case B2F_TVL1_SCALE_STEP: *v = P.scale_step; break;
+        case B2F_TVL1_GAMMA: *v = P.gamma; break;
+        case B2F_TVL1_USE_INITIAL_FLOW: *v = P.use_initial_flow; break;
+        default: return B2F_BAD_ARG;
+    }
+    return B2F_OK;
+}
+
+}  // namespace
+
+}  // namespace b2f
+
+extern "C" {
+
+void b2f_tvl1_default_params(b2f_tvl1_params *p) {
+    if (!p) return;
+    p->tau = 0.25;
+    p->lambda = 0.15;
+    p->theta = 0.3;
+    p->nscales = 5;
+    p->warps = 5;
+    p->epsilon = 0.01;
+    p->iterations = 300;
+    p->scale_step = 0.8;
+    p->gamma = 0.0;
+    p->use_initial_flow = 0;
+}
+
+int b2f_tvl1_create(const b2f_tvl1_params *p, b2f_handle **out) {
+    if (!out) return B2F_BAD_ARG;
+    b2f_tvl1_params d;
+    b2f_tvl1_default_params(&d);
+    if (p) d = *p;
+    *out = new (std::nothrow) b2f::Tvl1Engine(d);
+    return *out ? B2F_OK : B2F_OUT_OF_MEMORY;
+}
+
+}  // extern "C"
