@@ -1,0 +1,752 @@
+// farneback.cu -- cv::cuda::FarnebackOpticalFlow re-implemented for sm_100a.
+//
+// Reference being replaced (paths relative to /root/reference/modules/cudaoptflow):
+//   host  src/farneback.cpp:167-482   (calc / calcImpl, prepareGaussian, updateFlow_*)
+//   dev   src/cuda/farneback.cu:66-595 (polynomialExpansion, updateMatrices, updateFlow,
+//                                       boxFilter5, gaussianBlur, gaussianBlur5)
+// plus cv::cuda::resize / pyrDown / split / merge and cv::getGaussianKernel (opencv imgproc).
+//
+// What is different by design (same results, fewer bytes):
+//  * level images: the reference blurs the FULL-RES frame with up to 79 taps and then samples it
+//    bilinearly (farneback.cpp:445-452), 12 full-frame separable blurs per pair.  Here the
+//    vertical pass is evaluated only on the rows the bilinear sampling needs and the horizontal
+//    pass only at the columns it needs (identical tap order and arithmetic per sample);
+//  * one kernel per inner iteration: blur(M) -> updateFlow -> updateMatrices fused, the blurred M
+//    never reaches HBM and the flow is only written by the level's last iteration;
+//  * all tables live in the handle's arena (the reference's __constant__ tables are global state,
+//    farneback.cu:60-63,154,453);
+//  * one stream, no host synchronisation (the reference syncs per level, farneback.cpp:366,457).
+//
+// Kernel classes: 0 iter (blur5+updateFlow+updateMatrices), 1 polyexp, 2 level_image (convert,
+// sparse blur, resize / pyrDown), 3 update_matrices0, 4 flow_init (prolong / split / merge).
+#include "common.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace b2f {
+
+namespace {
+
+enum { CLS_ITER = 0, CLS_POLY = 1, CLS_IMG = 2, CLS_UPD0 = 3, CLS_FLOW = 4 };
+constexpr int MIN_SIZE = 32;  // farneback.cpp:54
+constexpr int BORDER_SIZE = 5;
+
+// 5 planes stacked vertically in one pitched image (row k*h + y), as the reference's R / M.
+struct Stack5 {
+    float *p;
+    int pitch, h;
+    __host__ __device__ __forceinline__ float &at(int k, int y, int x) const {
+        return p[((size_t)k * h + y) * pitch + x];
+    }
+};
+
+struct PolyTabs {
+    float g[8], xg[8], xxg[8];
+    float ig11, ig03, ig33, ig55;
+};
+
+// ------------------------------------------------------------------------------------------
+// host-side tables
+// ------------------------------------------------------------------------------------------
+// cv::getGaussianKernel(n, sigma, CV_32F) (opencv imgproc; farneback.cpp:445,462 call sites).
+void gaussian_kernel(int n, double sigma, std::vector<float> &out) {
+    static const double tab1[] = {1.0};
+    static const double tab3[] = {0.25, 0.5, 0.25};
+    static const double tab5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625};
+    static const double tab7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
+    const double *fixed = nullptr;
+    if (n % 2 == 1 && n <= 7 && sigma <= 0) fixed = n == 1 ? tab1 : n == 3 ? tab3 : n == 5 ? tab5 : tab7;
+    const double sigmaX = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+    const double scale2X = -0.5 / (sigmaX * sigmaX);
+    std::vector<double> cf(n);
+    double sum = 0;
+    for (int i = 0; i < n; ++i) {
+        const double x = i - (n - 1) * 0.5;
+        const double t = fixed ? fixed[i] : std::exp(scale2X * x * x);
+        cf[i] = t;
+        sum += t;
+    }
+    sum = 1.0 / sum;
+    out.resize(n);
+    for (int i = 0; i < n; ++i) out[i] = static_cast<float>(cf[i] * sum);
+}
+
+// In-place inverse of a symmetric positive-definite 6x6 via Cholesky (DECOMP_CHOLESKY).
+bool cholesky_inverse6(double A[6][6]) {
+    const int n = 6;
+    double L[6][6] = {};
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            double s = A[i][j];
+            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+            if (i == j) {
+                if (s <= 0) return false;
+                L[i][i] = std::sqrt(s);
+            } else {
+                L[i][j] = s / L[j][j];
+            }
+        }
+    }
+    double inv[6][6];
+    for (int c = 0; c < n; ++c) {
+        double y[6], x[6];
+        for (int i = 0; i < n; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+            y[i] = s / L[i][i];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = y[i];
+            for (int k = i + 1; k < n; ++k) s -= L[k][i] * x[k];
+            x[i] = s / L[i][i];
+        }
+        for (int i = 0; i < n; ++i) inv[i][c] = x[i];
+    }
+    std::memcpy(A, inv, sizeof(inv));
+    return true;
+}
+
+// FarnebackOpticalFlowImpl::prepareGaussian + setPolynomialExpansionConsts (farneback.cpp:209-276).
+bool prepare_poly_tabs(int n, double sigma, PolyTabs &T) {
+    if (sigma < FLT_EPSILON) sigma = n * 0.3;
+    float gbuf[15], xgbuf[15], xxgbuf[15];
+    float *g = gbuf + n, *xg = xgbuf + n, *xxg = xxgbuf + n;
+    double s = 0.;
+    for (int x = -n; x <= n; x++) {
+        g[x] = (float)std::exp(-x * x / (2 * sigma * sigma));
+        s += g[x];
+    }
+    s = 1. / s;
+    for (int x = -n; x <= n; x++) {
+        g[x] = (float)(g[x] * s);
+        xg[x] = (float)(x * g[x]);
+        xxg[x] = (float)(x * x * g[x]);
+    }
+    double G[6][6] = {};
+    for (int y = -n; y <= n; y++) {
+        for (int x = -n; x <= n; x++) {
+            G[0][0] += g[y] * g[x];
+            G[1][1] += g[y] * g[x] * x * x;
+            G[3][3] += g[y] * g[x] * x * x * x * x;
+            G[5][5] += g[y] * g[x] * x * x * y * y;
+        }
+    }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    if (!cholesky_inverse6(G)) return false;
+    std::memset(&T, 0, sizeof(T));
+    for (int i = 0; i <= n; ++i) {
+        T.g[i] = g[i];
+        T.xg[i] = xg[i];
+        T.xxg[i] = xxg[i];
+    }
+    T.ig11 = static_cast<float>(G[1][1]);
+    T.ig03 = static_cast<float>(G[0][3]);
+    T.ig33 = static_cast<float>(G[3][3]);
+    T.ig55 = static_cast<float>(G[5][5]);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+    // BrdReflect101: idx_low = |i| % n ... (single reflection is enough for |i| < 2n; loop for safety)
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * n - 2 - i;
+    }
+    return i;
+}
+
+// ------------------------------------------------------------------------------------------
+// level image, sparse Gaussian pre-blur (replaces gaussianBlurGpu(full frame) + cuda::resize,
+// farneback.cpp:445-452; kernel arithmetic farneback.cu:455-492, resize.cu:234-269).
+// V pass: Vbuf(2*y + t, x) = sum_j g[j] * (src(ry(sy - j), x) + src(ry(sy + j), x)),  sy = y1 / y2r.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_farn_blur_v(Plane f0, Plane f1, int rows, int cols, Plane v0, Plane v1,
+                                                     int lrows, float inv_fy, const float *__restrict__ g,
+                                                     int khalf, int identity) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int vy = blockIdx.y;  // 0 .. 2*lrows-1
+    if (x >= cols) return;
+    const int y = vy >> 1, t = vy & 1;
+    int sy;
+    if (identity) {
+        if (t) return;
+        sy = y;
+    } else {
+        const float src_y = y * inv_fy;
+        const int y1 = __float2int_rd(src_y);
+        if (t && (src_y - y1) == 0.f) return;  // zero bilinear weight: row never contributes
+        sy = t ? min(y1 + 1, rows - 1) : min(y1, rows - 1);
+    }
+    const Plane src = blockIdx.z ? f1 : f0;
+    float acc = __ldg(&src.at(sy, x)) * g[0];
+    for (int j = 1; j <= khalf; ++j)
+        acc += (__ldg(&src.at(reflect101(sy - j, rows), x)) + __ldg(&src.at(reflect101(sy + j, rows), x))) * g[j];
+    (blockIdx.z ? v1 : v0).at(vy, x) = acc;
+}
+
+__device__ __forceinline__ float farn_hblur(const Plane &v, int vy, int sx, int cols, const float *__restrict__ g,
+                                            int khalf) {
+    float res = v.at(vy, sx) * g[0];
+    for (int i = 1; i <= khalf; ++i)
+        res += (v.at(vy, reflect101(sx - i, cols)) + v.at(vy, reflect101(sx + i, cols))) * g[i];
+    return res;
+}
+
+__global__ void __launch_bounds__(256) k_farn_blur_h_resize(Plane v0, Plane v1, int rows, int cols, Plane d0, Plane d1,
+                                                            int lrows, int lcols, float inv_fx, float inv_fy,
+                                                            const float *__restrict__ g, int khalf, int identity) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= lcols || y >= lrows) return;
+    const Plane v = blockIdx.z ? v1 : v0;
+    float out;
+    if (identity) {
+        out = farn_hblur(v, 2 * y, x, cols, g, khalf);
+    } else {
+        const float src_x = x * inv_fx, src_y = y * inv_fy;
+        const int x1 = __float2int_rd(src_x), y1 = __float2int_rd(src_y);
+        const int x2 = x1 + 1, y2 = y1 + 1;
+        const int x1r = min(x1, cols - 1), x2r = min(x2, cols - 1);
+        const float wx2 = x2 - src_x, wx1 = src_x - x1;
+        const float wy2 = y2 - src_y, wy1 = src_y - y1;
+        out = 0.f;
+        // same accumulation order as resize_linear; zero-weight taps add exactly 0 and are skipped
+        out = out + farn_hblur(v, 2 * y, x1r, cols, g, khalf) * (wx2 * wy2);
+        if (wx1 != 0.f) out = out + farn_hblur(v, 2 * y, x2r, cols, g, khalf) * (wx1 * wy2);
+        if (wy1 != 0.f) {
+            out = out + farn_hblur(v, 2 * y + 1, x1r, cols, g, khalf) * (wx2 * wy1);
+            if (wx1 != 0.f) out = out + farn_hblur(v, 2 * y + 1, x2r, cols, g, khalf) * (wx1 * wy1);
+        }
+    }
+    (blockIdx.z ? d1 : d0).at(y, x) = out;
+}
+
+// ------------------------------------------------------------------------------------------
+// polynomial expansion (farneback.cu:66-119), both frames per launch.
+// Block = 32 x 8 output pixels.  Vertical pass for the 32+2n columns of the block into shared
+// memory (3 moments), then the horizontal pass; replicate clamping as the reference.
+// ------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256) k_farn_polyexp(Plane s0, Plane s1, Stack5 r0, Stack5 r1, int rows, int cols,
+                                                      PolyTabs T) {
+    constexpr int TW = 32, TH = 8, SW = TW + 2 * N;
+    __shared__ float sm[3][TH][SW];
+    const Plane src = blockIdx.z ? s1 : s0;
+    const Stack5 dst = blockIdx.z ? r1 : r0;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int x0 = blockIdx.x * TW, y = blockIdx.y * TH + ty;
+    if (y < rows) {
+        for (int i = tx; i < SW; i += TW) {
+            const int xc = clampi(x0 + i - N, 0, cols - 1);
+            float a0 = __ldg(&src.at(y, xc)) * T.g[0], a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float t0 = __ldg(&src.at(max(y - k, 0), xc));
+                const float t1 = __ldg(&src.at(min(y + k, rows - 1), xc));
+                a0 += T.g[k] * (t0 + t1);
+                a1 += T.xg[k] * (t1 - t0);
+                a2 += T.xxg[k] * (t0 + t1);
+            }
+            sm[0][ty][i] = a0;
+            sm[1][ty][i] = a1;
+            sm[2][ty][i] = a2;
+        }
+    }
+    __syncthreads();
+    const int x = x0 + tx;
+    if (y >= rows || x >= cols) return;
+    const float *row0 = &sm[0][ty][tx + N], *row1 = &sm[1][ty][tx + N], *row2 = &sm[2][ty][tx + N];
+    float b1 = T.g[0] * row0[0], b3 = T.g[0] * row1[0], b5 = T.g[0] * row2[0];
+    float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+#pragma unroll
+    for (int k = 1; k <= N; ++k) {
+        b1 += (row0[k] + row0[-k]) * T.g[k];
+        b4 += (row0[k] + row0[-k]) * T.xxg[k];
+        b2 += (row0[k] - row0[-k]) * T.xg[k];
+        b3 += (row1[k] + row1[-k]) * T.g[k];
+        b6 += (row1[k] - row1[-k]) * T.xg[k];
+        b5 += (row2[k] + row2[-k]) * T.g[k];
+    }
+    dst.at(0, y, x) = b3 * T.ig11;
+    dst.at(1, y, x) = b2 * T.ig11;
+    dst.at(2, y, x) = b1 * T.ig03 + b5 * T.ig33;
+    dst.at(3, y, x) = b1 * T.ig03 + b4 * T.ig33;
+    dst.at(4, y, x) = b6 * T.ig55;
+}
+
+// ------------------------------------------------------------------------------------------
+// updateMatrices for one pixel (farneback.cu:156-241).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float farn_border_w(int d) {
+    // c_border = {0.14, 0.14, 0.4472, 0.4472, 0.4472, 1} (farneback.cu:246)
+    return d <= 1 ? 0.14f : (d < BORDER_SIZE ? 0.4472f : 1.f);
+}
+
+__device__ __forceinline__ void farn_update_matrices_px(const Stack5 &R0, const Stack5 &R1, int rows, int cols, int x,
+                                                        int y, float dx, float dy, float (&m)[5]) {
+    float fx = x + dx, fy = y + dy;
+    // floorf of a wild flow must not overflow the int conversion
+    const float ffx = fminf(fmaxf(floorf(fx), -4.f), (float)cols + 4.f);
+    const float ffy = fminf(fmaxf(floorf(fy), -4.f), (float)rows + 4.f);
+    const int x1 = (int)ffx, y1 = (int)ffy;
+    fx -= floorf(fx);
+    fy -= floorf(fy);
+    float r2, r3, r4, r5, r6;
+    if (x1 >= 0 && y1 >= 0 && x1 < cols - 1 && y1 < rows - 1) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy);
+        const float a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const float *p = &R1.at(0, y1, x1);
+        const size_t ps = (size_t)R1.h * R1.pitch;
+        const int pitch = R1.pitch;
+        r2 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        p += ps;
+        r3 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        p += ps;
+        r4 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        p += ps;
+        r5 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        p += ps;
+        r6 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + pitch) + a11 * __ldg(p + pitch + 1);
+        r4 = (__ldg(&R0.at(2, y, x)) + r4) * 0.5f;
+        r5 = (__ldg(&R0.at(3, y, x)) + r5) * 0.5f;
+        r6 = (__ldg(&R0.at(4, y, x)) + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = __ldg(&R0.at(2, y, x));
+        r5 = __ldg(&R0.at(3, y, x));
+        r6 = __ldg(&R0.at(4, y, x)) * 0.5f;
+    }
+    r2 = (__ldg(&R0.at(0, y, x)) - r2) * 0.5f;
+    r3 = (__ldg(&R0.at(1, y, x)) - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    const float scale = farn_border_w(min(x, BORDER_SIZE)) * farn_border_w(min(y, BORDER_SIZE)) *
+                        farn_border_w(min(cols - x - 1, BORDER_SIZE)) * farn_border_w(min(rows - y - 1, BORDER_SIZE));
+    r2 *= scale; r3 *= scale; r4 *= scale; r5 *= scale; r6 *= scale;
+    m[0] = r4 * r4 + r6 * r6;
+    m[1] = (r4 + r5) * r6;
+    m[2] = r5 * r5 + r6 * r6;
+    m[3] = r4 * r2 + r6 * r3;
+    m[4] = r6 * r2 + r5 * r3;
+}
+
+__global__ void __launch_bounds__(256) k_farn_update_matrices(Plane flowx, Plane flowy, Stack5 R0, Stack5 R1, Stack5 M,
+                                                              int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    float m[5];
+    farn_update_matrices_px(R0, R1, rows, cols, x, y, flowx.at(y, x), flowy.at(y, x), m);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) M.at(k, y, x) = m[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// fused inner iteration: blur5(M) -> updateFlow -> updateMatrices
+// (boxFilter5 farneback.cu:357-412 / gaussianBlur5 :539-595, updateFlow :267-286, updateMatrices).
+// Block = 64 x 8 output pixels, 256 threads (each thread: 2 pixels in x).  The vertical pass is
+// computed for the 64 + 2k columns of the block straight from M (L1/L2 hits, replicate clamp) into
+// shared memory; the horizontal pass, the 2x2 solve and the matrix update run from there.
+// GAUSS = false: plain sums then * 1/area.  GAUSS = true: taps g[] (replicate border).
+// ------------------------------------------------------------------------------------------
+constexpr int IT_TW = 64, IT_TH = 8;
+
+template <bool GAUSS>
+__global__ void __launch_bounds__(256) k_farn_iter(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
+                                                   Plane flowy, int rows, int cols, int khalf, float box_inv,
+                                                   const float *__restrict__ g, int update_matrices,
+                                                   int write_flow) {
+    extern __shared__ float sm[];  // [5][IT_TH][sw]
+    const int sw = IT_TW + 2 * khalf;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * IT_TW, y0 = blockIdx.y * IT_TH;
+
+    // vertical pass: (column i, row r) pairs spread over the block
+    for (int idx = tid; idx < sw * IT_TH; idx += 256) {
+        const int r = idx / sw, i = idx - r * sw;
+        const int y = y0 + r;
+        if (y >= rows) continue;
+        const int xc = clampi(x0 + i - khalf, 0, cols - 1);
+        float acc[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float c = __ldg(&Min.at(k, y, xc));
+            acc[k] = GAUSS ? c * g[0] : c;
+        }
+        for (int j = 1; j <= khalf; ++j) {
+            const int ya = max(y - j, 0), yb = min(y + j, rows - 1);
+            const float gj = GAUSS ? g[j] : 1.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float s = __ldg(&Min.at(k, ya, xc)) + __ldg(&Min.at(k, yb, xc));
+                acc[k] = GAUSS ? acc[k] + s * gj : acc[k] + s;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sm[(k * IT_TH + r) * sw + i] = acc[k];
+    }
+    __syncthreads();
+
+    const int r = tid >> 5;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int lx = (tid & 31) + 32 * half;
+        const int x = x0 + lx, y = y0 + r;
+        if (x >= cols || y >= rows) continue;
+        float res[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float *row = &sm[(k * IT_TH + r) * sw + lx + khalf];
+            float a = GAUSS ? row[0] * g[0] : row[0];
+            for (int i = 1; i <= khalf; ++i) a = GAUSS ? a + (row[-i] + row[i]) * g[i] : a + (row[-i] + row[i]);
+            res[k] = GAUSS ? a : a * box_inv;
+        }
+        // updateFlow
+        const float g11 = res[0], g12 = res[1], g22 = res[2], h1 = res[3], h2 = res[4];
+        const float detInv = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+        const float fx = (g11 * h2 - g12 * h1) * detInv;
+        const float fy = (g22 * h1 - g12 * h2) * detInv;
+        if (write_flow) {
+            flowx.at(y, x) = fx;
+            flowy.at(y, x) = fy;
+        }
+        if (update_matrices) {
+            float m[5];
+            farn_update_matrices_px(R0, R1, rows, cols, x, y, fx, fy, m);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) Mout.at(k, y, x) = m[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host engine
+// ------------------------------------------------------------------------------------------
+struct FLevel {
+    int rows = 0, cols = 0;
+    double scale = 1.0;
+    int ksize = 3;         // pyramid pre-blur size (smoothSize)
+    size_t taps_off = 0;   // offset (floats) of the half kernel in the device table
+    Plane img[2];          // level image, both frames (fastPyramids: pyramid level)
+    Plane fx, fy;          // flow at this level
+};
+
+class FarnebackEngine : public b2f_handle {
+public:
+    explicit FarnebackEngine(const b2f_farneback_params &p) : P(p) { algo = ALGO_FARNEBACK; }
+    b2f_farneback_params P;
+
+    int calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, cudaStream_t s) override;
+    int set_param(int id, double v) override;
+    int get_param(int id, double *v) const override;
+    const char *default_name() const override { return "DenseOpticalFlow.FarnebackOpticalFlow"; }
+    const char *class_name(int cls) const override {
+        static const char *n[] = {"farn_iter", "farn_polyexp", "farn_level_image", "farn_update_matrices0",
+                                  "farn_flow_init"};
+        return (cls >= 0 && cls < 5) ? n[cls] : "";
+    }
+    size_t workspace_bytes(int rows, int cols, int type) override {
+        (void)type;
+        Layout L;
+        std::vector<float> tabs;
+        return layout(rows, cols, true, L, tabs);
+    }
+
+private:
+    struct Layout {
+        int rows = 0, cols = 0;
+        b2f_farneback_params P{};
+        std::vector<FLevel> levels;  // index k = pyramid level (0 = full res)
+        Plane frames[2];
+        Plane vbuf[2];
+        Stack5 R[2], M[2];
+        float *tabs_dev = nullptr;
+        size_t tabs_count = 0;
+        size_t win_taps_off = 0;  // GAUSSIAN flag: window kernel
+        PolyTabs poly;
+    };
+    Layout L_;
+
+    size_t layout(int rows, int cols, bool counting, Layout &L, std::vector<float> &tabs);
+    cudaError_t ensure_workspace(int rows, int cols);
+};
+
+size_t FarnebackEngine::layout(int rows, int cols, bool counting, Layout &L, std::vector<float> &tabs) {
+    Arena tmp;
+    Arena &A = counting ? tmp : arena;
+    A.begin(counting);
+    L.rows = rows;
+    L.cols = cols;
+    L.P = P;
+    L.levels.clear();
+    tabs.clear();
+
+    // crop levels, farneback.cpp:333-340
+    double scale = 1;
+    int cropped = 0;
+    for (; cropped < P.num_levels; cropped++) {
+        scale *= P.pyr_scale;
+        if (cols * scale < MIN_SIZE || rows * scale < MIN_SIZE) break;
+    }
+    L.frames[0] = A.plane(rows, cols);
+    L.frames[1] = A.plane(rows, cols);
+    int max_lrows = 0;
+    int pr = rows, pc = cols;
+    for (int k = 0; k <= cropped; ++k) {
+        FLevel lv;
+        scale = 1;
+        for (int i = 0; i < k; i++) scale *= P.pyr_scale;
+        lv.scale = scale;
+        const double sigma = (1. / scale - 1) * 0.5;  // farneback.cpp:372-374
+        int smooth = cv_round(sigma * 5) | 1;
+        smooth = smooth > 3 ? smooth : 3;
+        lv.ksize = smooth;
+        if (P.fast_pyramids) {  // pyrDown sizes, pyramids.cpp:66-93
+            if (k > 0) {
+                pr = (pr + 1) / 2;
+                pc = (pc + 1) / 2;
+            }
+            lv.rows = pr;
+            lv.cols = pc;
+        } else {
+            lv.cols = cv_round(cols * scale);
+            lv.rows = cv_round(rows * scale);
+            if (lv.cols < 1) lv.cols = 1;
+            if (lv.rows < 1) lv.rows = 1;
+            std::vector<float> gk;
+            gaussian_kernel(smooth, sigma, gk);
+            lv.taps_off = tabs.size();
+            for (int i = smooth / 2; i < smooth; ++i) tabs.push_back(gk[i]);
+        }
+        if (k == 0 && P.fast_pyramids) {
+            lv.img[0] = L.frames[0];
+            lv.img[1] = L.frames[1];
+        } else {
+            lv.img[0] = A.plane(lv.rows, lv.cols);
+            lv.img[1] = A.plane(lv.rows, lv.cols);
+        }
+        lv.fx = A.plane(lv.rows, lv.cols);
+        lv.fy = A.plane(lv.rows, lv.cols);
+        if (lv.rows > max_lrows) max_lrows = lv.rows;
+        L.levels.push_back(lv);
+    }
+    if (P.flags & B2F_OPTFLOW_FARNEBACK_GAUSSIAN) {  // farneback.cpp:460-464
+        std::vector<float> gk;
+        gaussian_kernel(P.win_size, static_cast<double>(static_cast<float>(P.win_size / 2 * 0.3f)), gk);
+        L.win_taps_off = tabs.size();
+        for (int i = P.win_size / 2; i < P.win_size; ++i) tabs.push_back(gk[i]);
+    }
+    if (tabs.empty()) tabs.push_back(0.f);
+    L.tabs_count = tabs.size();
+    if (!P.fast_pyramids) {
+        L.vbuf[0] = A.plane(2 * max_lrows, cols);
+        L.vbuf[1] = A.plane(2 * max_lrows, cols);
+    }
+    for (int i = 0; i < 2; ++i) {
+        Plane r = A.plane(5 * rows, cols), m = A.plane(5 * rows, cols);
+        L.R[i] = Stack5{r.p, r.pitch, rows};
+        L.M[i] = Stack5{m.p, m.pitch, rows};
+    }
+    L.tabs_dev = static_cast<float *>(A.bytes(sizeof(float) * tabs.size()));
+    return A.used();
+}
+
+cudaError_t FarnebackEngine::ensure_workspace(int rows, int cols) {
+    if (L_.rows == rows && L_.cols == cols && std::memcmp(&L_.P, &P, sizeof(P)) == 0 && arena.capacity() > 0)
+        return cudaSuccess;
+    Layout tmp;
+    std::vector<float> tabs;
+    const size_t need = layout(rows, cols, true, tmp, tabs);
+    cudaError_t e = arena.reserve(need);
+    if (e != cudaSuccess) return e;
+    layout(rows, cols, false, L_, tabs);
+    if (!prepare_poly_tabs(P.poly_n, P.poly_sigma, L_.poly)) return cudaErrorInvalidValue;
+    // one-time synchronous table upload (the reference re-uploads __constant__ tables every call)
+    return cudaMemcpy(L_.tabs_dev, tabs.data(), sizeof(float) * tabs.size(), cudaMemcpyHostToDevice);
+}
+
+int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, cudaStream_t s) {
+    // preconditions: farneback.cpp:173-174,181-182,316-317
+    if (!(I0->type == B2F_8UC1 || I0->type == B2F_32FC1)) return B2F_UNSUPPORTED_TYPE;
+    if (I0->type != I1->type) return B2F_UNSUPPORTED_TYPE;
+    if (I0->rows != I1->rows || I0->cols != I1->cols) return B2F_SIZE_MISMATCH;
+    if (flow->type != B2F_32FC2) return B2F_UNSUPPORTED_TYPE;
+    if (flow->rows != I0->rows || flow->cols != I0->cols) return B2F_SIZE_MISMATCH;
+    if (!(P.poly_n == 5 || P.poly_n == 7)) return B2F_BAD_ARG;
+    if (P.fast_pyramids && !(std::abs(P.pyr_scale - 0.5) < 1e-6)) return B2F_BAD_ARG;
+    if (P.num_levels < 0 || P.num_iters < 0 || P.win_size < 1 || (P.win_size & 1) == 0) return B2F_BAD_ARG;
+    if (!(P.pyr_scale > 0.0 && P.pyr_scale < 1.0)) return B2F_BAD_ARG;
+    const size_t es = I0->type == B2F_8UC1 ? 1 : 4;
+    if (I0->step < I0->cols * es || I1->step < I1->cols * es || flow->step < (size_t)flow->cols * 8) return B2F_BAD_ARG;
+
+    const int rows = I0->rows, cols = I0->cols;
+    Ctx c = make_ctx(s);
+    c.check(ensure_workspace(rows, cols));
+    if (!c.ok()) return finish(c, s);
+    Layout &L = L_;
+    const int top = static_cast<int>(L.levels.size()) - 1;
+    stats.levels = top + 1;
+    stats.iterations_run = 0;
+
+    const ImageView v0{I0->data, I0->step, rows, cols, I0->type};
+    const ImageView v1{I1->data, I1->step, rows, cols, I1->type};
+    const ImageView vf{flow->data, flow->step, rows, cols, B2F_32FC2};
+    const dim3 block(32, 8);
+
+    convert_pair(c, CLS_IMG, v0, v1, L.frames[0], L.frames[1], 1.0f);  // convertTo(CV_32F), farneback.cpp:342-345
+    if (P.fast_pyramids) {
+        for (int k = 1; k <= top; ++k)
+            for (int i = 0; i < 2; ++i)
+                pyr_down(c, CLS_IMG, L.levels[k - 1].img[i], L.levels[k - 1].rows, L.levels[k - 1].cols,
+                         L.levels[k].img[i], L.levels[k].rows, L.levels[k].cols);
+    }
+    if (P.flags & B2F_OPTFLOW_USE_INITIAL_FLOW) split_flow(c, CLS_FLOW, vf, L.levels[0].fx, L.levels[0].fy);
+
+    const int khalf = P.win_size / 2;
+    const float box_inv = 1.f / ((1 + 2 * khalf) * (1 + 2 * khalf));
+    const bool gauss = (P.flags & B2F_OPTFLOW_FARNEBACK_GAUSSIAN) != 0;
+    const float *win_taps = L.tabs_dev + L.win_taps_off;
+
+    for (int k = top; k >= 0; --k) {
+        FLevel &lv = L.levels[k];
+        const int h = lv.rows, w = lv.cols;
+        const double npx = (double)h * w;
+        const dim3 grid(div_up(w, 32), div_up(h, 8));
+
+        // ---- flow initialisation, farneback.cpp:396-417 ----
+        if (k == top) {
+            if (P.flags & B2F_OPTFLOW_USE_INITIAL_FLOW) {
+                if (k > 0)
+                    resize_linear_pair(c, CLS_FLOW, L.levels[0].fx, L.levels[0].fy, rows, cols, lv.fx, lv.fy, h, w,
+                                       inv_scale_from_sizes(cols, w), inv_scale_from_sizes(rows, h),
+                                       static_cast<float>(lv.scale));
+            } else {
+                fill_plane(c, lv.fx, h, w, 0.f);
+                fill_plane(c, lv.fy, h, w, 0.f);
+            }
+        } else {
+            const FLevel &pv = L.levels[k + 1];
+            resize_linear_pair(c, CLS_FLOW, pv.fx, pv.fy, pv.rows, pv.cols, lv.fx, lv.fy, h, w,
+                               inv_scale_from_sizes(pv.cols, w), inv_scale_from_sizes(pv.rows, h),
+                               static_cast<float>(1. / P.pyr_scale));
+        }
+
+        // ---- level images ----
+        if (!P.fast_pyramids) {
+            const int kh = lv.ksize / 2;
+            const float *taps = L.tabs_dev + lv.taps_off;
+            const int identity = (h == rows && w == cols) ? 1 : 0;  // resize.cpp:90-94 copy path
+            const float inv_fx = inv_scale_from_sizes(cols, w), inv_fy = inv_scale_from_sizes(rows, h);
+            const dim3 gv(div_up(cols, 256), 2 * h, 2);
+            B2F_LAUNCH(c, CLS_IMG, 2.0 * 4.0 * ((double)rows * cols + 2.0 * h * cols), k_farn_blur_v, gv, dim3(256), 0,
+                       L.frames[0], L.frames[1], rows, cols, L.vbuf[0], L.vbuf[1], h, inv_fy, taps, kh, identity);
+            const dim3 gh(div_up(w, 32), div_up(h, 8), 2);
+            B2F_LAUNCH(c, CLS_IMG, 2.0 * 4.0 * (2.0 * h * cols + npx), k_farn_blur_h_resize, gh, block, 0, L.vbuf[0],
+                       L.vbuf[1], rows, cols, lv.img[0], lv.img[1], h, w, inv_fx, inv_fy, taps, kh, identity);
+        }
+
+        // ---- polynomial expansion of both frames ----
+        Stack5 R0{L.R[0].p, plane_pitch(w), h}, R1{L.R[1].p, plane_pitch(w), h};
+        Stack5 Ma{L.M[0].p, plane_pitch(w), h}, Mb{L.M[1].p, plane_pitch(w), h};
+        {
+            const dim3 gp(div_up(w, 32), div_up(h, 8), 2);
+            const double bytes = 2.0 * 24.0 * npx;
+            Plane a{lv.img[0].p, lv.img[0].pitch}, b{lv.img[1].p, lv.img[1].pitch};
+            if (P.poly_n == 5)
+                B2F_LAUNCH(c, CLS_POLY, bytes, k_farn_polyexp<5>, gp, block, 0, a, b, R0, R1, h, w, L.poly);
+            else
+                B2F_LAUNCH(c, CLS_POLY, bytes, k_farn_polyexp<7>, gp, block, 0, a, b, R0, R1, h, w, L.poly);
+        }
+
+        // ---- initial matrices, then the fused iterations ----
+        B2F_LAUNCH(c, CLS_UPD0, 68.0 * npx, k_farn_update_matrices, grid, block, 0, lv.fx, lv.fy, R0, R1, Ma, h, w);
+        const dim3 gi(div_up(w, IT_TW), div_up(h, IT_TH));
+        const size_t smem = sizeof(float) * 5 * IT_TH * (IT_TW + 2 * khalf);
+        for (int i = 0; i < P.num_iters; ++i) {
+            const int upd = i < P.num_iters - 1;  // farneback.cpp:468-470
+            const int wflow = !upd;
+            const double bytes = npx * (20.0 + (upd ? 60.0 : 0.0) + (wflow ? 8.0 : 0.0));
+            if (gauss)
+                B2F_LAUNCH(c, CLS_ITER, bytes, k_farn_iter<true>, gi, dim3(256), smem, Ma, Mb, R0, R1, lv.fx, lv.fy, h,
+                           w, khalf, box_inv, win_taps, upd, wflow);
+            else
+                B2F_LAUNCH(c, CLS_ITER, bytes, k_farn_iter<false>, gi, dim3(256), smem, Ma, Mb, R0, R1, lv.fx, lv.fy,
+                           h, w, khalf, box_inv, win_taps, upd, wflow);
+            Stack5 t = Ma;
+            Ma = Mb;
+            Mb = t;
+            stats.iterations_run++;
+        }
+    }
+
+    merge_flow(c, CLS_FLOW, L.levels[0].fx, L.levels[0].fy, vf);  // farneback.cpp:197-198
+    return finish(c, s);
+}
+
+int FarnebackEngine::set_param(int id, double v) {
+    switch (id) {
+        case B2F_FARN_NUM_LEVELS: P.num_levels = static_cast<int>(v); break;
+        case B2F_FARN_PYR_SCALE: P.pyr_scale = v; break;
+        case B2F_FARN_FAST_PYRAMIDS: P.fast_pyramids = v != 0; break;
+        case B2F_FARN_WIN_SIZE: P.win_size = static_cast<int>(v); break;
+        case B2F_FARN_NUM_ITERS: P.num_iters = static_cast<int>(v); break;
+        case B2F_FARN_POLY_N: P.poly_n = static_cast<int>(v); break;
+        case B2F_FARN_POLY_SIGMA: P.poly_sigma = v; break;
+        case B2F_FARN_FLAGS: P.flags = static_cast<int>(v); break;
+        default: return B2F_BAD_ARG;
+    }
+    return B2F_OK;
+}
+
+int FarnebackEngine::get_param(int id, double *v) const {
+    switch (id) {
+        case B2F_FARN_NUM_LEVELS: *v = P.num_levels; break;
+        case B2F_FARN_PYR_SCALE: *v = P.pyr_scale; break;
+        case B2F_FARN_FAST_PYRAMIDS: *v = P.fast_pyramids; break;
+        case B2F_FARN_WIN_SIZE: *v = P.win_size; break;
+        case B2F_FARN_NUM_ITERS: *v = P.num_iters; break;
+        case B2F_FARN_POLY_N: *v = P.poly_n; break;
+        case B2F_FARN_POLY_SIGMA: *v = P.poly_sigma; break;
+        case B2F_FARN_FLAGS: *v = P.flags; break;
+        default: return B2F_BAD_ARG;
+    }
+    return B2F_OK;
+}
+
+}  // namespace
+
+}  // namespace b2f
+
+extern "C" {
+
+void b2f_farneback_default_params(b2f_farneback_params *p) {
+    if (!p) return;
+    p->num_levels = 5;
+    p->pyr_scale = 0.5;
+    p->fast_pyramids = 0;
+    p->win_size = 13;
+    p->num_iters = 10;
+    p->poly_n = 5;
+    p->poly_sigma = 1.1;
+    p->flags = 0;
+}
+
+int b2f_farneback_create(const b2f_farneback_params *p, b2f_handle **out) {
+    if (!out) return B2F_BAD_ARG;
+    b2f_farneback_params d;
+    b2f_farneback_default_params(&d);
+    if (p) d = *p;
+    *out = new (std::nothrow) b2f::FarnebackEngine(d);
+    return *out ? B2F_OK : B2F_OUT_OF_MEMORY;
+}
+
+}  // extern "C"

@@ -23,14 +23,4 @@ int b2f_denselk_create(const b2f_denselk_params *, b2f_handle **out) {
     return B2F_UNSUPPORTED_TYPE;
 }
 
-void b2f_farneback_default_params(b2f_farneback_params *p) {
-    if (!p) return;
-    p->num_levels = 5; p->pyr_scale = 0.5; p->fast_pyramids = 0; p->win_size = 13;
-    p->num_iters = 10; p->poly_n = 5; p->poly_sigma = 1.1; p->flags = 0;
-}
-int b2f_farneback_create(const b2f_farneback_params *, b2f_handle **out) {
-    if (out) *out = nullptr;
-    return B2F_UNSUPPORTED_TYPE;
-}
-
 }  // extern "C"

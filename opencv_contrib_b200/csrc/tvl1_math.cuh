@@ -5,7 +5,7 @@
 //   estimateUKernel             modules/cudaoptflow/src/cuda/tvl1flow.cu:209-288
 //   estimateDualVariablesKernel modules/cudaoptflow/src/cuda/tvl1flow.cu:313-348
 // Deliberate arithmetic choices (documented in DESIGN.md, covered by the tolerance tests):
-//   * -rho/grad uses the fast division (MUFU.RCP, <= 2 ulp) instead of an IEEE divide;
+//   * -rho/grad is -rho * rcp.approx(grad) (MUFU.RCP, <= 2 ulp) instead of an IEEE divide;
 //   * hypotf(a,b) is sqrt.approx(a*a + b*b) and the dual normalisation multiplies by
 //     rcp.approx(1 + taut*g) instead of two IEEE divides;
 //   * the divergence at the first row/column uses a zero ghost value, (p - 0) + (q - q_up), where
@@ -25,15 +25,14 @@ struct Tvl1Scalars {
 #ifdef __CUDACC__
 
 // Thresholding step TH: returns the multiplier fi such that d = fi * (Ix, Iy, gamma).
+// Branch-free (selects only): a per-pixel divergent branch around the reciprocal serialises the
+// eight pixels a thread owns in the blocked kernel.
 __device__ __forceinline__ float tvl1_threshold(float rho, float grad, float l_t) {
     const float lg = __fmul_rn(l_t, grad);
-    float fi = 0.f;
-    if (rho < -lg)
-        fi = l_t;
-    else if (rho > lg)
-        fi = -l_t;
-    else if (grad > FLT_EPSILON)
-        fi = __fdividef(-rho, grad);
+    const float q = __fmul_rn(-rho, rcp_approx(grad));  // garbage when grad == 0, discarded below
+    float fi = grad > FLT_EPSILON ? q : 0.f;
+    fi = rho > lg ? -l_t : fi;
+    fi = rho < -lg ? l_t : fi;
     return fi;
 }
 

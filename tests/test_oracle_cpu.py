@@ -1,0 +1,100 @@
+"""CPU tests (no GPU): the oracles against the live reference pieces available in this image
+(cv2.calcOpticalFlowFarneback, cv2.resize/remap/getGaussianKernel) and against ground truth."""
+import numpy as np
+import cv2
+import pytest
+
+from oracle import synth, metrics, tvl1_cpu, tvl1_gpu_model as gm, farneback_gpu_model as fm
+
+
+def test_level_sizes_match_survey():
+    # 1080p TV-L1 levels (saturate_cast<int> = round half to even)
+    sizes, ns = gm.level_sizes(1080, 1920, 5, 0.8)
+    assert ns == 5
+    assert sizes == [(1080, 1920), (864, 1536), (691, 1229), (553, 983), (442, 786)]
+    sizes, ns = gm.level_sizes(2160, 3840, 5, 0.8)
+    assert sizes == [(2160, 3840), (1728, 3072), (1382, 2458), (1106, 1966), (885, 1573)]
+    # <16 px stop rule (tvl1flow.cpp:243-247)
+    sizes, ns = gm.level_sizes(40, 40, 8, 0.5)
+    assert ns == 2 and sizes[-1] == (10, 10)
+
+
+def test_cv_round_half_even():
+    assert [gm.cv_round(v) for v in (2.5, 7.5, 67.5, 3.5, -0.5)] == [2, 8, 68, 4, 0]
+
+
+def test_tvl1_cpu_oracle_recovers_known_flow():
+    # criterion of the reference's CPU regression test (test_tvl1optflow.cpp:114-142):
+    # >= 95 % of pixels with EPE <= 0.1 -- here against exact synthetic ground truth.
+    I0, I1, gt = synth.make_pair(120, 160, seed=0, kind="const")
+    P = tvl1_cpu.TVL1Params(warps=5, epsilon=0.0, innerIterations=1, outerIterations=30, medianFiltering=1)
+    f = tvl1_cpu.calc(I0, I1, P)
+    st = metrics.epe_stats(f, gt, border=16)
+    assert st["frac_le_0.1"] >= 0.95 and st["mean"] < 0.05, st
+
+
+def test_tvl1_cpu_oracle_defaults_with_median_and_early_exit():
+    I0, I1, gt = synth.make_pair(96, 128, seed=1, kind="const")
+    f = tvl1_cpu.calc(I0, I1, tvl1_cpu.TVL1Params())  # defaults: median 5, eps 0.01, 10 x 30
+    st = metrics.epe_stats(f, gt, border=16)
+    assert st["frac_le_0.1"] >= 0.95, st
+
+
+def test_tvl1_cuda_semantics_model_close_to_cpu_oracle():
+    # the reference's own GPU-vs-CPU test maps iterations the same way (test_optflow.cpp:456-460)
+    I0, I1, gt = synth.make_pair(120, 160, seed=2, kind="affine")
+    fc = tvl1_cpu.calc(I0, I1, tvl1_cpu.TVL1Params(warps=5, epsilon=0.0, innerIterations=1, outerIterations=30,
+                                                   medianFiltering=1))
+    fg = gm.calc(I0, I1, gm.TVL1Params(warps=5, epsilon=0.0, iterations=30))
+    st = metrics.epe_stats(fc, fg, border=16)
+    assert st["frac_le_0.1"] >= 0.95 and st["mean"] < 0.1, st
+
+
+def test_tvl1_model_gamma_and_f32_run():
+    I0, I1, gt = synth.make_pair(64, 80, seed=3, kind="const", dtype="f32")
+    f = gm.calc(I0, I1, gm.TVL1Params(nscales=3, warps=2, epsilon=0.0, iterations=10, gamma=1.0))
+    assert np.isfinite(f).all()
+
+
+def test_tvl1_model_error_cadence_trace():
+    I0, I1, _ = synth.make_pair(64, 80, seed=4, kind="const")
+    tr = []
+    gm.calc(I0, I1, gm.TVL1Params(nscales=2, warps=2, epsilon=0.05, iterations=50), trace=tr)
+    # sampled only on odd n -> a warp that exits early stops after an even number of iterations
+    for lvl in tr:
+        for n in lvl:
+            assert n == 50 or n % 2 == 0
+
+
+@pytest.mark.parametrize("kw,ncc_tol,epe_tol", [
+    (dict(), 1e-4, 0.02),                      # box filter: reference tolerance 1e-4 (test_optflow.cpp:341-348)
+    (dict(polyN=7, polySigma=1.5, pyrScale=0.8, numLevels=3), 1e-4, 0.02),
+    (dict(flags=256), 2e-2, 0.2),              # gaussian: reference tolerance 2e-2
+])
+def test_farneback_model_vs_live_cv2(kw, ncc_tol, epe_tol):
+    I0, I1, gt = synth.make_pair(160, 200, seed=5, kind="smooth")
+    f = fm.calc(I0, I1, fm.FarnebackParams(**kw))
+    c = cv2.calcOpticalFlowFarneback(I0, I1, None, kw.get("pyrScale", 0.5), kw.get("numLevels", 5), 13, 10,
+                                     kw.get("polyN", 5), kw.get("polySigma", 1.1), kw.get("flags", 0))
+    assert metrics.ncc_dissimilarity(f, c) <= ncc_tol
+    assert metrics.epe_stats(f, c)["mean"] <= epe_tol
+
+
+def test_farneback_prepare_gaussian_closed_form():
+    g, xg, xxg, ig11, ig03, ig33, ig55 = fm.prepare_gaussian(5, 1.1)
+    assert abs(float(g[0] + 2 * g[1:].sum()) - 1.0) < 1e-6
+    assert ig11 > 0 and ig33 > 0 and ig55 > 0 and ig03 < 0
+
+
+def test_pyr_down_model_is_cv2():
+    a = synth.texture(37, 51, 0)
+    d = fm.pyr_down(a)
+    assert d.shape == (19, 26)
+
+
+def test_synth_pair_sign_convention():
+    # I0(x) ~= I1(x + flow): cv2 Farneback on a constant shift must recover (+2.5, -1.25)
+    I0, I1, gt = synth.make_pair(120, 160, seed=0, kind="const")
+    c = cv2.calcOpticalFlowFarneback(I0, I1, None, 0.5, 3, 15, 5, 5, 1.1, 0)
+    med = np.median(c[20:-20, 20:-20].reshape(-1, 2), axis=0)
+    assert abs(med[0] - 2.5) < 0.2 and abs(med[1] + 1.25) < 0.2
