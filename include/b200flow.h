@@ -145,7 +145,8 @@ typedef enum b2f_param_id {
     /* engine knobs (no reference counterpart) */
     B2F_ENGINE_FUSED_ITERS = 900, /* TV-L1: inner iterations fused per HBM pass (0 = auto)     */
     B2F_ENGINE_USE_GRAPH = 901,   /* capture the fixed schedule in a CUDA graph (default 1)    */
-    B2F_ENGINE_KERNEL_PATH = 902  /* 0 = auto, 1 = unfused reference-shaped kernels (debug)    */
+    B2F_ENGINE_KERNEL_PATH = 902  /* TV-L1: 0 = auto (persistent TMA kernel), 1 = unfused
+                                     reference-shaped kernels, 2 = blocked kernel without TMA   */
 } b2f_param_id;
 
 B2F_API int b2f_set_param(b2f_handle *h, int id, double value);

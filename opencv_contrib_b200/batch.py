@@ -1,0 +1,104 @@
+"""Batched frame-pair front end: shards independent image pairs over streams on one GPU and over
+ranks on one node (one process per GPU).
+
+The reference has no batching or multi-GPU layer -- callers loop over ``calc`` and pick a device
+with ``cv::cuda::setDevice`` (modules/cudaoptflow/test/test_optflow.cpp:58-63, and the 16-stream
+``cv::parallel_for_`` pattern of test_optflow.cpp:468-528).  Frame pairs are independent problems,
+so the path shards with NO data-path collective: rank r of R owns the contiguous block
+[r*N/R, (r+1)*N/R) of pair indices; NCCL appears only in ``gather_flows``, the
+result gather to rank 0.
+
+torch is plumbing here (device tensors, streams, torch.distributed); all compute is in
+libb200flow.so.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Callable, List, Sequence, Tuple
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block partition [lo, hi) of n_items over world ranks (remainder to low ranks)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+class FlowBatcher:
+    """Runs many independent pairs through ``n_streams`` engine instances (one handle per stream,
+    as instances are not re-entrant: reference tvl1flow.cpp:141-167 caches buffers per instance)."""
+
+    def __init__(self, factory: Callable[[], object], n_streams: int = 4, device=None):
+        import torch
+        self.torch = torch
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.algs = [factory() for _ in range(n_streams)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        self._done = [torch.cuda.Event() for _ in range(n_streams)]
+        self._start = torch.cuda.Event()
+
+    @property
+    def n_streams(self) -> int:
+        return len(self.streams)
+
+    def run_device(self, pairs: Sequence[Tuple[object, object]], flows: Sequence[object]) -> None:
+        """Device-resident batch.  Work is forked from / joined to the CURRENT stream, so CUDA
+        events recorded on it bracket the whole batch; no host synchronisation."""
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.device)
+        self._start.record(cur)
+        used = min(self.n_streams, len(pairs))
+        for s in self.streams[:used]:
+            s.wait_event(self._start)
+        for i, ((a, b), f) in enumerate(zip(pairs, flows)):
+            k = i % self.n_streams
+            self.algs[k].calc(a, b, f, self.streams[k])
+        for k in range(used):
+            self._done[k].record(self.streams[k])
+            cur.wait_event(self._done[k])
+
+    def run_host(self, pairs: Sequence[Tuple[object, object]], flows: Sequence[object]) -> None:
+        """Host-resident batch (numpy arrays, ideally pinned): each stream's worker thread uploads,
+        computes and downloads its share through b2f_calc_host, so copies of one pair overlap the
+        compute of others.  Returns when every flow has landed in host memory."""
+        errs: List[BaseException] = []
+
+        def work(k: int):
+            try:
+                for i in range(k, len(pairs), self.n_streams):
+                    a, b = pairs[i]
+                    self.algs[k].calc_host(a, b, flows[i], self.streams[k])
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(min(self.n_streams, len(pairs)))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def launches(self) -> int:
+        return sum(a.getStats()["launches"] for a in self.algs)
+
+    def reset_stats(self) -> None:
+        for a in self.algs:
+            a.resetStats()
+
+
+def gather_flows(local_flows, dst: int = 0, group=None):
+    """Result gather to rank ``dst`` (NCCL on GPUs, gloo on CPU tensors).  ``local_flows`` is one
+    stacked tensor (n_local, H, W, 2) with the same n_local on every rank.  Returns the list of
+    per-rank tensors on ``dst`` (index = rank, i.e. global pair order) and None elsewhere."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [local_flows]
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    out = None
+    if rank == dst:
+        out = [local_flows.new_empty(local_flows.shape) for _ in range(world)]
+    dist.gather(local_flows, out, dst=dst, group=group)
+    return out

@@ -16,6 +16,7 @@
 #include "tvl1_blocked.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -238,6 +239,7 @@ public:
     explicit Tvl1Engine(const b2f_tvl1_params &p) : P(p) { algo = ALGO_TVL1; }
     ~Tvl1Engine() override {
         if (err_host) cudaFreeHost(err_host);
+        free(tma_maps_);
         destroy_graph();
     }
 
@@ -272,6 +274,14 @@ private:
     };
     Layout L_;
     double *err_host = nullptr;
+    // TMA descriptor blocks, [level][direction], built once per workspace (host memory, 64 B aligned)
+    void *tma_maps_ = nullptr;
+    bool tma_ok_ = false;
+    int num_sms_ = 0;
+    const void *tma_maps(int level, int cur) const {
+        return static_cast<const char *>(tma_maps_) + (size_t)(level * 2 + cur) * tvl1_tma_maps_bytes();
+    }
+    void blocked_planes(int s, Tvl1BlockedPlanes &B) const;
 
     // graph cache (fixed schedule only)
     cudaGraphExec_t graph_exec_ = nullptr;
@@ -362,7 +372,44 @@ cudaError_t Tvl1Engine::ensure_workspace(int rows, int cols) {
     if (e != cudaSuccess) return e;
     layout(rows, cols, false, L_);
     if (!err_host) e = cudaMallocHost(&err_host, sizeof(double) * 4);
-    return e;
+    if (e != cudaSuccess) return e;
+    // TMA descriptors for every solved level and both ping-pong directions
+    if (!num_sms_) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms_ <= 0) num_sms_ = 148;
+    }
+    free(tma_maps_);
+    tma_maps_ = nullptr;
+    tma_ok_ = false;
+    if (!L_.gamma) {
+        const size_t mb = tvl1_tma_maps_bytes();
+        const size_t total = (mb * 2 * L_.nscales + 63) & ~size_t(63);
+        tma_maps_ = aligned_alloc(64, total);
+        tma_ok_ = tma_maps_ != nullptr;
+        for (int s = 0; tma_ok_ && s < L_.nscales; ++s) {
+            Tvl1BlockedPlanes B;
+            blocked_planes(s, B);
+            for (int cur = 0; tma_ok_ && cur < 2; ++cur)
+                tma_ok_ = tvl1_tma_build_maps(const_cast<void *>(tma_maps(s, cur)), B, cur, L_.levels[s].rows,
+                                              L_.levels[s].cols);
+        }
+    }
+    return cudaSuccess;
+}
+
+void Tvl1Engine::blocked_planes(int s, Tvl1BlockedPlanes &B) const {
+    const Level &lv = L_.levels[s];
+    const int cols = lv.cols;
+    B.I1wx = shared_plane(SH_I1WX, cols); B.I1wy = shared_plane(SH_I1WY, cols);
+    B.grad = shared_plane(SH_GRAD, cols); B.rho_c = shared_plane(SH_RHO, cols);
+    B.s[0].u1 = lv.u1; B.s[0].u2 = lv.u2;
+    B.s[0].p11 = shared_plane(SH_P11, cols); B.s[0].p12 = shared_plane(SH_P12, cols);
+    B.s[0].p21 = shared_plane(SH_P21, cols); B.s[0].p22 = shared_plane(SH_P22, cols);
+    B.s[1].u1 = shared_plane(SH_U1B, cols); B.s[1].u2 = shared_plane(SH_U2B, cols);
+    B.s[1].p11 = shared_plane(SH_P11B, cols); B.s[1].p12 = shared_plane(SH_P12B, cols);
+    B.s[1].p21 = shared_plane(SH_P21B, cols); B.s[1].p22 = shared_plane(SH_P22B, cols);
 }
 
 void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
@@ -411,14 +458,8 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
     const bool blocked_ok = fixed_schedule && !use_gamma && knobs.kernel_path != 1;
 
     Tvl1BlockedPlanes B;
-    if (blocked_ok) {
-        B.I1wx = T.I1wx; B.I1wy = T.I1wy; B.grad = T.grad; B.rho_c = T.rho_c;
-        B.s[0].u1 = T.u1; B.s[0].u2 = T.u2;
-        B.s[0].p11 = T.p11; B.s[0].p12 = T.p12; B.s[0].p21 = T.p21; B.s[0].p22 = T.p22;
-        B.s[1].u1 = shared_plane(SH_U1B, cols); B.s[1].u2 = shared_plane(SH_U2B, cols);
-        B.s[1].p11 = shared_plane(SH_P11B, cols); B.s[1].p12 = shared_plane(SH_P12B, cols);
-        B.s[1].p21 = shared_plane(SH_P21B, cols); B.s[1].p22 = shared_plane(SH_P22B, cols);
-    }
+    if (blocked_ok) blocked_planes(s, B);
+    const bool use_tma = blocked_ok && tma_ok_ && knobs.kernel_path != 2;
     int cur = 0;  // which state set holds the current (u, p) in the blocked path
 
     for (int w = 0; w < P.warps; ++w) {
@@ -431,7 +472,10 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
             int done = 0;
             while (done < P.iterations) {
                 const int kk = tvl1_blocked_pick_k(knobs.fused_iters, P.iterations - done, rows, cols);
-                tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);
+                if (use_tma)
+                    tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
+                else
+                    tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);
                 cur ^= 1;
                 done += kk;
             }

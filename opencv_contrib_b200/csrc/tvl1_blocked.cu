@@ -1,6 +1,8 @@
 // tvl1_blocked.cu -- see tvl1_blocked.cuh for the design.
 #include "tvl1_blocked.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 namespace b2f {
 
 namespace {
@@ -185,6 +187,205 @@ __global__ void __launch_bounds__(NT, 1)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Persistent TMA variant.  One CTA per SM walks its tiles; the 10 input planes of a region arrive
+// through cp.async.bulk.tensor (zero fill outside the image = the border ghost values), the next
+// region is prefetched into the same staging buffer as soon as the current one sits in registers,
+// so the HBM stream overlaps the K iterations; results leave as 8-byte vector stores straight
+// from registers (they drain while the next tile computes).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+struct TmaMaps {
+    CUtensorMap in[N_IN];
+};
+
+__device__ __forceinline__ void store_pairs(const Plane &P, int gy, int gx, const float (&v)[4], bool ok0, bool ok1,
+                                            int cols) {
+    float *row = P.row(gy) + gx;
+    if (ok0) {
+        if (gx + 1 < cols) *reinterpret_cast<float2 *>(row) = make_float2(v[0], v[1]);
+        else row[0] = v[0];
+    }
+    if (ok1) {
+        if (gx + 3 < cols) *reinterpret_cast<float2 *>(row + 2) = make_float2(v[2], v[3]);
+        else row[2] = v[2];
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1)
+    k_tvl1_blocked_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12,
+                       Plane o_p21, Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int tile,
+                       int tiles_x, int ntiles) {
+    extern __shared__ __align__(1024) float smem[];
+    float *stage = smem;
+    float *ex = smem + N_IN * PLANE_F;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ex + 4 * EX_F);
+
+    const int tid = threadIdx.x;
+    const int lx = tid & 15, tr = tid >> 4;
+    constexpr uint32_t kStageBytes = N_IN * PLANE_F * sizeof(float);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int t = blockIdx.x;
+    if (tid == 0 && t < ntiles) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        mbar_expect_tx(bar, kStageBytes);
+#pragma unroll
+        for (int pl = 0; pl < N_IN; ++pl)
+            tma_load_2d(stage + pl * PLANE_F, &maps.in[pl], tx * tile - halo, ty * tile - halo, bar);
+    }
+    uint32_t parity = 0;
+    for (; t < ntiles; t += gridDim.x) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int gx0 = tx * tile - halo, gy0 = ty * tile - halo;
+        mbar_wait(bar, parity);
+        parity ^= 1;
+
+        Regs r;
+        {
+            const int o0 = (2 * tr) * R + 4 * lx, o1 = o0 + R;
+            ld4(stage + 0 * PLANE_F + o0, r.Ix[0]);  ld4(stage + 0 * PLANE_F + o1, r.Ix[1]);
+            ld4(stage + 1 * PLANE_F + o0, r.Iy[0]);  ld4(stage + 1 * PLANE_F + o1, r.Iy[1]);
+            ld4(stage + 2 * PLANE_F + o0, r.gr[0]);  ld4(stage + 2 * PLANE_F + o1, r.gr[1]);
+            ld4(stage + 3 * PLANE_F + o0, r.rc[0]);  ld4(stage + 3 * PLANE_F + o1, r.rc[1]);
+            ld4(stage + 4 * PLANE_F + o0, r.u1[0]);  ld4(stage + 4 * PLANE_F + o1, r.u1[1]);
+            ld4(stage + 5 * PLANE_F + o0, r.u2[0]);  ld4(stage + 5 * PLANE_F + o1, r.u2[1]);
+            ld4(stage + 6 * PLANE_F + o0, r.p11[0]); ld4(stage + 6 * PLANE_F + o1, r.p11[1]);
+            ld4(stage + 7 * PLANE_F + o0, r.p12[0]); ld4(stage + 7 * PLANE_F + o1, r.p12[1]);
+            ld4(stage + 8 * PLANE_F + o0, r.p21[0]); ld4(stage + 8 * PLANE_F + o1, r.p21[1]);
+            ld4(stage + 9 * PLANE_F + o0, r.p22[0]); ld4(stage + 9 * PLANE_F + o1, r.p22[1]);
+        }
+        __syncthreads();  // the staging buffer is free again
+
+        const int tn = t + gridDim.x;
+        if (tid == 0 && tn < ntiles) {
+            const int ny = tn / tiles_x, nx = tn - ny * tiles_x;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, kStageBytes);
+#pragma unroll
+            for (int pl = 0; pl < N_IN; ++pl)
+                tma_load_2d(stage + pl * PLANE_F, &maps.in[pl], nx * tile - halo, ny * tile - halo, bar);
+        }
+
+        const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
+        const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
+        if (border)
+            tile_iterate<true>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
+        else
+            tile_iterate<false>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
+
+        // centre tile -> global, 8-byte stores (halo, tile and gx0 are even, so pairs never straddle)
+        const int rx = 4 * lx;
+        const bool okx0 = rx >= halo && rx < R - halo && gxb < cols;
+        const bool okx1 = rx + 2 >= halo && rx + 2 < R - halo && gxb + 2 < cols;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int ry = 2 * tr + j, gy = gyb + j;
+            if (ry >= halo && ry < R - halo && gy < rows) {
+                store_pairs(o_u1, gy, gxb, r.u1[j], okx0, okx1, cols);
+                store_pairs(o_u2, gy, gxb, r.u2[j], okx0, okx1, cols);
+                store_pairs(o_p11, gy, gxb, r.p11[j], okx0, okx1, cols);
+                store_pairs(o_p12, gy, gxb, r.p12[j], okx0, okx1, cols);
+                store_pairs(o_p21, gy, gxb, r.p21[j], okx0, okx1, cols);
+                store_pairs(o_p22, gy, gxb, r.p22[j], okx0, okx1, cols);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side of the TMA variant
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool encode_plane(CUtensorMap *m, const Plane &P, int rows, int cols) {
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)P.pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)R, (cuuint32_t)R};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, P.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t tvl1_tma_maps_bytes() { return sizeof(TmaMaps); }
+
+bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int rows, int cols) {
+    TmaMaps *m = static_cast<TmaMaps *>(dst);
+    const Tvl1State &si = B.s[cur];
+    const Plane in[N_IN] = {B.I1wx, B.I1wy, B.grad, B.rho_c, si.u1, si.u2, si.p11, si.p12, si.p21, si.p22};
+    for (int i = 0; i < N_IN; ++i)
+        if (!encode_plane(&m->in[i], in[i], rows, cols)) return false;
+    return true;
+}
+
+constexpr size_t SMEM_TMA_BYTES = sizeof(float) * (size_t)(N_IN * PLANE_F + 4 * EX_F) + 64;
+
+void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                     const Tvl1Scalars &k, int iters, int num_sms) {
+    const Tvl1State &so = B.s[cur ^ 1];
+    const int halo = (iters + 1) & ~1;  // even halo >= iters keeps every store 8-byte aligned
+    const int tile = R - 2 * halo;
+    const int tiles_x = div_up(cols, tile), tiles_y = div_up(rows, tile);
+    const int ntiles = tiles_x * tiles_y;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    const double bytes = 64.0 * (double)rows * cols * iters;
+    B2F_LAUNCH(c, cls, bytes, k_tvl1_blocked_tma, dim3(grid), dim3(NT), SMEM_TMA_BYTES,
+               *static_cast<const TmaMaps *>(maps), so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
+               halo, tile, tiles_x, ntiles);
+}
+
+namespace {
 }  // namespace
 
 cudaError_t tvl1_blocked_init() {
@@ -194,6 +395,9 @@ cudaError_t tvl1_blocked_init() {
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
     e = cudaFuncSetAttribute(k_tvl1_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)SMEM_TMA_BYTES);
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }
@@ -201,7 +405,7 @@ cudaError_t tvl1_blocked_init() {
 int tvl1_blocked_pick_k(int knob, int remaining, int rows, int cols) {
     (void)rows;
     (void)cols;
-    int kk = knob > 0 ? knob : 5;
+    int kk = knob > 0 ? knob : 6;
     if (kk > TVL1_KMAX) kk = TVL1_KMAX;
     if (kk > remaining) kk = remaining;
     return kk;

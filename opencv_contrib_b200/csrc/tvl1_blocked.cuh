@@ -43,4 +43,12 @@ int tvl1_blocked_pick_k(int knob, int remaining, int rows, int cols);
 void tvl1_blocked_launch(Ctx &c, int cls, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                          const Tvl1Scalars &k, int iters);
 
+
+// ---- persistent TMA variant ----
+// Opaque per-(level, direction) descriptor block (10 CUtensorMaps), built once per workspace.
+size_t tvl1_tma_maps_bytes();
+bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int rows, int cols);
+void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                     const Tvl1Scalars &k, int iters, int num_sms);
+
 }  // namespace b2f

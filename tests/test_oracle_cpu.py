@@ -98,3 +98,20 @@ def test_synth_pair_sign_convention():
     c = cv2.calcOpticalFlowFarneback(I0, I1, None, 0.5, 3, 15, 5, 5, 1.1, 0)
     med = np.median(c[20:-20, 20:-20].reshape(-1, 2), axis=0)
     assert abs(med[0] - 2.5) < 0.2 and abs(med[1] + 1.25) < 0.2
+
+
+def test_golden_fixtures_pin_the_oracles():
+    """tests/golden/farneback_*.npz were produced by the live CPU reference (make_golden.py);
+    the cv2 on this box and the CUDA-semantics model must both agree with them."""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    names = sorted(n for n in os.listdir(gold) if n.startswith("farneback_") and n.endswith(".npz"))
+    assert len(names) >= 4
+    for n in names:
+        z = np.load(os.path.join(gold, n))
+        kw = {k[3:]: z[k].item() for k in z.files if k.startswith("kw_")}
+        live = cv2.calcOpticalFlowFarneback(z["I0"], z["I1"], None, kw.get("pyrScale", 0.5), kw.get("numLevels", 5),
+                                            13, 10, kw.get("polyN", 5), kw.get("polySigma", 1.1), kw.get("flags", 0))
+        assert metrics.ncc_dissimilarity(live, z["flow"]) <= 1e-6, n
+        model = fm.calc(z["I0"], z["I1"], fm.FarnebackParams(**kw))
+        assert metrics.ncc_dissimilarity(model, z["flow"]) <= float(z["ncc_tol"]), n

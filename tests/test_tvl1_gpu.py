@@ -1,0 +1,209 @@
+"""GPU parity tests for OpticalFlowDual_TVL1 (through the C ABI via ctypes).
+
+Tolerances (stated, measured on B200 in round 1 -- see DESIGN.md "Parity"):
+  * engine vs the CUDA-semantics numpy model: max |dflow| <= 1e-3 px (gamma = 0);
+  * engine vs the CPU reference oracle (modules/optflow semantics): >= 95 % of interior pixels
+    with EPE <= 0.1 px, mean EPE <= 0.08 px, NCC dissimilarity <= 4e-3
+    (reference criteria: test_tvl1optflow.cpp:114-142, test_optflow.cpp:462-465);
+  * temporally blocked kernel vs unfused kernels: bit-identical;
+  * concurrent instances on separate streams vs synchronous: bit-identical (test_optflow.cpp:468-528).
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import synth, metrics, tvl1_cpu, tvl1_gpu_model as gm
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(dev, I0, I1, path=0, fused=0, graph=1, stream=None, init=None, **kw):
+    import torch
+    import opencv_contrib_b200 as ocb
+    alg = ocb.OpticalFlowDual_TVL1_create(**kw)
+    alg.setEngineOption("kernel_path", path)
+    alg.setEngineOption("fused_iters", fused)
+    alg.setEngineOption("use_graph", graph)
+    d0, d1 = torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev)
+    fl = None if init is None else torch.from_numpy(init.copy()).to(dev)
+    f = alg.calc(d0, d1, fl, stream)
+    torch.cuda.synchronize()
+    return f.cpu().numpy(), alg
+
+
+@pytest.mark.parametrize("h,w,kind,seed", [(120, 160, "const", 0), (243, 317, "smooth", 1), (97, 131, "affine", 2)])
+def test_engine_matches_cuda_semantics_model(cuda_device, h, w, kind, seed):
+    I0, I1, gt = synth.make_pair(h, w, seed=seed, kind=kind)
+    kw = dict(nscales=4, warps=3, epsilon=0.0, iterations=20)
+    ref = gm.calc(I0, I1, gm.TVL1Params(**kw))
+    for path in (1, 2, 0):
+        got, alg = _run(cuda_device, I0, I1, path=path, **kw)
+        st = metrics.epe_stats(got, ref)
+        assert np.isfinite(got).all() and st["max"] <= 1e-3, (path, st)
+    assert alg.getStats()["launches"] > 0
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 6, 7, 10, 12])
+def test_blocked_kernel_bit_identical_to_unfused(cuda_device, K):
+    # odd sizes: tiles straddle every image border
+    I0, I1, _ = synth.make_pair(203, 277, seed=3, kind="smooth")
+    kw = dict(nscales=3, warps=2, epsilon=0.0, iterations=23)
+    a, _ = _run(cuda_device, I0, I1, path=1, **kw)
+    for path in (0, 2):          # 0 = persistent TMA kernel, 2 = blocked kernel with plain loads
+        for graph in (0, 1):
+            b, _ = _run(cuda_device, I0, I1, path=path, fused=K, graph=graph, **kw)
+            assert np.array_equal(a, b), (path, K, graph, float(np.abs(a - b).max()))
+
+
+def test_engine_vs_cpu_reference_oracle_epe(cuda_device):
+    # parameter mapping of the reference's own GPU-vs-CPU test (test_optflow.cpp:448-460)
+    I0, I1, gt = synth.make_pair(240, 320, seed=4, kind="smooth")
+    got, _ = _run(cuda_device, I0, I1, nscales=5, warps=5, epsilon=0.0, iterations=30)
+    cpu = tvl1_cpu.calc(I0, I1, tvl1_cpu.TVL1Params(nscales=5, warps=5, epsilon=0.0, innerIterations=1,
+                                                    outerIterations=30, medianFiltering=1))
+    st = metrics.epe_stats(got, cpu, border=16)
+    ncc = metrics.ncc_dissimilarity(got[16:-16, 16:-16], cpu[16:-16, 16:-16])
+    assert st["frac_le_0.1"] >= 0.95 and st["mean"] <= 0.08 and ncc <= 4e-3, (st, ncc)
+
+
+def test_default_epsilon_cadence_matches_model(cuda_device):
+    I0, I1, _ = synth.make_pair(120, 160, seed=2, kind="const")
+    kw = dict(nscales=3, warps=3, epsilon=0.01, iterations=100)
+    tr = []
+    ref = gm.calc(I0, I1, gm.TVL1Params(**kw), trace=tr)
+    got, alg = _run(cuda_device, I0, I1, **kw)
+    assert metrics.epe_stats(got, ref)["max"] <= 1e-3
+    assert alg.getStats()["iterations_run"] == sum(sum(t) for t in tr)
+
+
+def test_gamma_illumination_path(cuda_device):
+    # gamma != 0 is chaotic (1e-7 input noise moves the model by ~0.1 px at a few pixels), so the
+    # tolerance is statistical
+    I0, I1, _ = synth.make_pair(120, 160, seed=2, kind="const")
+    kw = dict(nscales=3, warps=3, epsilon=0.0, iterations=20, gamma=1.0)
+    ref = gm.calc(I0, I1, gm.TVL1Params(**kw))
+    got, _ = _run(cuda_device, I0, I1, **kw)
+    st = metrics.epe_stats(got, ref)
+    assert st["mean"] <= 5e-3 and st["frac_le_0.1"] >= 0.99, st
+
+
+def test_float_input_and_initial_flow(cuda_device):
+    I0, I1, gt = synth.make_pair(120, 160, seed=5, kind="const", dtype="f32")
+    kw = dict(nscales=3, warps=3, epsilon=0.0, iterations=20)
+    ref = gm.calc(I0, I1, gm.TVL1Params(**kw))
+    got, _ = _run(cuda_device, I0, I1, **kw)
+    assert metrics.epe_stats(got, ref)["max"] <= 1e-3
+    init = (gt + 0.25).astype(np.float32)
+    kw["useInitialFlow"] = True
+    ref = gm.calc(I0, I1, gm.TVL1Params(**kw), init_flow=init)
+    got, _ = _run(cuda_device, I0, I1, init=init, **kw)
+    assert metrics.epe_stats(got, ref)["max"] <= 1e-3
+
+
+def test_pitched_roi_inputs(cuda_device):
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(100, 140, seed=6, kind="const")
+    kw = dict(nscales=3, warps=2, epsilon=0.0, iterations=10)
+    a, _ = _run(cuda_device, I0, I1, **kw)
+    big0 = torch.zeros((128, 200), dtype=torch.uint8, device=cuda_device)
+    big1 = torch.zeros((128, 200), dtype=torch.uint8, device=cuda_device)
+    bigf = torch.zeros((128, 200, 2), dtype=torch.float32, device=cuda_device)
+    big0[7:107, 13:153] = torch.from_numpy(I0).to(cuda_device)
+    big1[7:107, 13:153] = torch.from_numpy(I1).to(cuda_device)
+    alg = ocb.OpticalFlowDual_TVL1_create(**kw)
+    alg.calc(big0[7:107, 13:153], big1[7:107, 13:153], bigf[7:107, 13:153])
+    torch.cuda.synchronize()
+    assert np.array_equal(bigf[7:107, 13:153].cpu().numpy(), a)
+    assert float(bigf[:7].abs().max()) == 0.0 and float(bigf[:, :13].abs().max()) == 0.0
+
+
+def test_concurrent_streams_bit_identical(cuda_device):
+    # reference: OpticalFlowDual_TVL1.Async (test_optflow.cpp:468-528)
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(160, 200, seed=7, kind="smooth")
+    kw = dict(nscales=3, warps=3, epsilon=0.0, iterations=20)
+    gold, _ = _run(cuda_device, I0, I1, **kw)
+    d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
+    n = 8
+    algs = [ocb.OpticalFlowDual_TVL1_create(**kw) for _ in range(n)]
+    streams = [torch.cuda.Stream(device=cuda_device) for _ in range(n)]
+    outs = [None] * n
+
+    def work(i):
+        outs[i] = algs[i].calc(d0, d1, None, streams[i])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    torch.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), gold)
+
+
+def test_stream_ordering_after_prior_work(cuda_device):
+    # reference: FarnebackOpticalFlowAsync (test_optflow.cpp:359-416): work enqueued on the caller's
+    # stream before calc must be visible to it
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(160, 200, seed=8, kind="const")
+    kw = dict(nscales=3, warps=2, epsilon=0.0, iterations=10)
+    gold, _ = _run(cuda_device, I0, I1, **kw)
+    s = torch.cuda.Stream(device=cuda_device)
+    h0, h1 = torch.from_numpy(I0).pin_memory(), torch.from_numpy(I1).pin_memory()
+    dummy = torch.empty(48 << 20, dtype=torch.uint8).pin_memory()
+    alg = ocb.OpticalFlowDual_TVL1_create(**kw)
+    with torch.cuda.stream(s):
+        big = dummy.to(cuda_device, non_blocking=True)
+        d0 = h0.to(cuda_device, non_blocking=True)
+        d1 = h1.to(cuda_device, non_blocking=True)
+        out = alg.calc(d0, d1, None, s)
+    s.synchronize()
+    assert np.array_equal(out.cpu().numpy(), gold) and big.numel() > 0
+
+
+def test_host_buffer_entry_point(cuda_device):
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(120, 160, seed=9, kind="const")
+    kw = dict(nscales=3, warps=2, epsilon=0.0, iterations=10)
+    gold, _ = _run(cuda_device, I0, I1, **kw)
+    alg = ocb.OpticalFlowDual_TVL1_create(**kw)
+    assert np.array_equal(alg.calc_host(I0, I1), gold)
+
+
+def test_error_codes(cuda_device):
+    import torch
+    import opencv_contrib_b200 as ocb
+    alg = ocb.OpticalFlowDual_TVL1_create()
+    a = torch.zeros((64, 64), dtype=torch.uint8, device=cuda_device)
+    b = torch.zeros((64, 65), dtype=torch.uint8, device=cuda_device)
+    with pytest.raises(ocb.B2FError) as e:
+        alg.calc(a, b)
+    assert e.value.status == 3                                    # size mismatch (tvl1flow.cpp:188)
+    with pytest.raises(ocb.B2FError) as e:
+        alg.calc(a, a.float())
+    assert e.value.status == 2                                    # type mismatch (tvl1flow.cpp:189)
+    with pytest.raises(ocb.B2FError) as e:
+        alg.calc(a.to(torch.int16), a.to(torch.int16))
+    assert e.value.status == 2                                    # only 8UC1 / 32FC1 (tvl1flow.cpp:187)
+    alg.setNumScales(0)
+    with pytest.raises(ocb.B2FError) as e:
+        alg.calc(a, a)
+    assert e.value.status == 1                                    # nscales > 0 (tvl1flow.cpp:191)
+
+
+def test_1080p_round_trip_properties(cuda_device):
+    """Full BASELINE size: size-independent checks (the numpy oracles would take minutes)."""
+    import torch
+    I0, I1, gt = synth.make_pair(1080, 1920, seed=0, kind="const")
+    kw = dict(nscales=5, warps=10, epsilon=0.0, iterations=30)
+    got, alg = _run(cuda_device, I0, I1, **kw)
+    assert np.isfinite(got).all() and alg.getStats()["levels"] == 5
+    st = metrics.epe_stats(got, gt, border=32)          # recovers the known translation
+    assert st["frac_le_0.1"] >= 0.95, st
+    z, _ = _run(cuda_device, I0, I0, **kw)              # identical frames -> zero flow
+    assert float(np.abs(z).max()) <= 1e-3
+    again, _ = _run(cuda_device, I0, I1, **kw)          # run-to-run determinism
+    assert np.array_equal(again, got)

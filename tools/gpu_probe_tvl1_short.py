@@ -8,7 +8,7 @@ I0, I1, gt = synth.make_pair(243, 317, seed=1, kind="smooth")
 kw = dict(nscales=4, warps=4, epsilon=0.0, iterations=30)
 ref = gm.calc(I0, I1, gm.TVL1Params(**kw))
 outs = {}
-for path, K in [(1, 0), (0, 1), (0, 5), (0, 7)]:
+for path, K in [(1, 0), (0, 1), (0, 5), (0, 6), (2, 6), (0, 7)]:
     alg = ocb.OpticalFlowDual_TVL1_create(**kw)
     alg.setEngineOption("kernel_path", path); alg.setEngineOption("fused_iters", K)
     f = alg.calc(torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev)); torch.cuda.synchronize()
@@ -18,7 +18,7 @@ for k, v in outs.items():
     print(k, "bit-equal to unfused:", np.array_equal(v, outs[(1, 0)]))
 I0, I1, gt = synth.make_pair(1080, 1920, seed=0, kind="smooth")
 d0, d1 = torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev)
-for (path, K, graph) in [(0, 3, 1), (0, 5, 1), (0, 6, 1), (0, 10, 1)]:
+for (path, K, graph) in [(0, 2, 1), (0, 4, 1), (0, 6, 1), (0, 8, 1), (0, 10, 1), (2, 6, 1), (0, 6, 0)]:
     alg = ocb.OpticalFlowDual_TVL1_create(nscales=5, warps=10, epsilon=0.0, iterations=30)
     alg.setEngineOption("kernel_path", path); alg.setEngineOption("fused_iters", K); alg.setEngineOption("use_graph", graph)
     flow = torch.empty((1080, 1920, 2), dtype=torch.float32, device=dev)
