@@ -428,6 +428,128 @@ __global__ void __launch_bounds__(256) k_farn_iter(Stack5 Min, Stack5 Mout, Stac
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Register-blocked variant of the fused iteration for a compile-time window half-size K
+// (winSize = 2K+1; K = 6 is the reference default 13).  Same arithmetic and summation order as
+// k_farn_iter, ~4x fewer instructions:
+//   vertical pass   one task = (column, plane, 16-row half): 16+2K loads feed 16 outputs from a
+//                   register window instead of 2K+1 loads per output;
+//   horizontal pass one task = (row, 4 consecutive pixels): 4 LDS.128 per plane feed 4 outputs;
+//   R0 / M / flow   move as float4.
+// Block = 64 x 32 output pixels, 256 threads, 5*32*(64+2K)*4 B shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int FT_W = 64, FT_H = 32;
+
+template <int K, bool GAUSS>
+__global__ void __launch_bounds__(256) k_farn_iter_fast(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
+                                                        Plane flowy, int rows, int cols, float box_inv,
+                                                        const float *__restrict__ g, int update_matrices,
+                                                        int write_flow) {
+    constexpr int SW = FT_W + 2 * K;  // staged columns (multiple of 4 for even K)
+    constexpr int HALF = FT_H / 2;
+    constexpr int WIN = HALF + 2 * K;
+    extern __shared__ __align__(16) float sm[];  // [5][FT_H][SW]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
+
+    float gk[K + 1];
+#pragma unroll
+    for (int j = 0; j <= K; ++j) gk[j] = GAUSS ? g[j] : 1.f;
+
+    // ---- vertical pass ----
+    for (int task = tid; task < SW * 5 * 2; task += 256) {
+        const int half = task / (SW * 5);
+        const int rem = task - half * (SW * 5);
+        const int pl = rem / SW, i = rem - pl * SW;
+        const int xc = clampi(x0 + i - K, 0, cols - 1);
+        const int yb = y0 + half * HALF - K;
+        float v[WIN];
+#pragma unroll
+        for (int q = 0; q < WIN; ++q) v[q] = __ldg(&Min.at(pl, clampi(yb + q, 0, rows - 1), xc));
+        float *dst = sm + ((size_t)pl * FT_H + half * HALF) * SW + i;
+#pragma unroll
+        for (int o = 0; o < HALF; ++o) {
+            float acc = GAUSS ? v[o + K] * gk[0] : v[o + K];
+#pragma unroll
+            for (int j = 1; j <= K; ++j) {
+                const float s2 = v[o + K - j] + v[o + K + j];
+                acc = GAUSS ? acc + s2 * gk[j] : acc + s2;
+            }
+            dst[o * SW] = acc;
+        }
+    }
+    __syncthreads();
+
+    // ---- horizontal pass + 2x2 solve + matrix update, 4 pixels per task ----
+#pragma unroll 1
+    for (int task = tid; task < FT_H * (FT_W / 4); task += 256) {
+        const int r = task / (FT_W / 4), q = task - r * (FT_W / 4);
+        const int y = y0 + r, x = x0 + 4 * q;
+        if (y >= rows || x >= cols) continue;
+        float res[5][4];
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl) {
+            const float *row = sm + ((size_t)pl * FT_H + r) * SW + 4 * q;
+            float w[4 + 2 * K + 2];
+#pragma unroll
+            for (int c = 0; c < (4 + 2 * K + 3) / 4; ++c) {
+                const float4 t = *reinterpret_cast<const float4 *>(row + 4 * c);
+                w[4 * c] = t.x;
+                w[4 * c + 1] = t.y;
+                if (4 * c + 2 < 4 + 2 * K + 2) w[4 * c + 2] = t.z;
+                if (4 * c + 3 < 4 + 2 * K + 2) w[4 * c + 3] = t.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float acc = GAUSS ? w[e + K] * gk[0] : w[e + K];
+#pragma unroll
+                for (int i = 1; i <= K; ++i) {
+                    const float s2 = w[e + K - i] + w[e + K + i];
+                    acc = GAUSS ? acc + s2 * gk[i] : acc + s2;
+                }
+                res[pl][e] = GAUSS ? acc : acc * box_inv;
+            }
+        }
+        float fx[4], fy[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float g11 = res[0][e], g12 = res[1][e], g22 = res[2][e], h1 = res[3][e], h2 = res[4][e];
+            const float detInv = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+            fx[e] = (g11 * h2 - g12 * h1) * detInv;
+            fy[e] = (g22 * h1 - g12 * h2) * detInv;
+        }
+        const bool full = x + 3 < cols;
+        if (write_flow) {
+            if (full) {
+                *reinterpret_cast<float4 *>(&flowx.at(y, x)) = make_float4(fx[0], fx[1], fx[2], fx[3]);
+                *reinterpret_cast<float4 *>(&flowy.at(y, x)) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+            } else {
+                for (int e = 0; e < 4 && x + e < cols; ++e) {
+                    flowx.at(y, x + e) = fx[e];
+                    flowy.at(y, x + e) = fy[e];
+                }
+            }
+        }
+        if (update_matrices) {
+            float m[4][5];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (x + e < cols) farn_update_matrices_px(R0, R1, rows, cols, x + e, y, fx[e], fy[e], m[e]);
+                else { m[e][0] = m[e][1] = m[e][2] = m[e][3] = m[e][4] = 0.f; }
+            }
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl) {
+                if (full) {
+                    *reinterpret_cast<float4 *>(&Mout.at(pl, y, x)) = make_float4(m[0][pl], m[1][pl], m[2][pl], m[3][pl]);
+                } else {
+                    for (int e = 0; e < 4 && x + e < cols; ++e) Mout.at(pl, y, x + e) = m[e][pl];
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host engine
 // ------------------------------------------------------------------------------------------
@@ -592,6 +714,17 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
     Ctx c = make_ctx(s);
     c.check(ensure_workspace(rows, cols));
     if (!c.ok()) return finish(c, s);
+    {
+        static bool attr_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+            const int bytes = (int)(sizeof(float) * 5 * FT_H * (FT_W + 12));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            attr_done[dev] = c.ok();
+        }
+    }
     Layout &L = L_;
     const int top = static_cast<int>(L.levels.size()) - 1;
     stats.levels = top + 1;
@@ -671,11 +804,21 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
         B2F_LAUNCH(c, CLS_UPD0, 68.0 * npx, k_farn_update_matrices, grid, block, 0, lv.fx, lv.fy, R0, R1, Ma, h, w);
         const dim3 gi(div_up(w, IT_TW), div_up(h, IT_TH));
         const size_t smem = sizeof(float) * 5 * IT_TH * (IT_TW + 2 * khalf);
+        const bool fast6 = khalf == 6 && knobs.kernel_path != 1;
+        const dim3 gf(div_up(w, FT_W), div_up(h, FT_H));
+        const size_t smem_fast = sizeof(float) * 5 * FT_H * (FT_W + 12);
         for (int i = 0; i < P.num_iters; ++i) {
             const int upd = i < P.num_iters - 1;  // farneback.cpp:468-470
             const int wflow = !upd;
             const double bytes = npx * (20.0 + (upd ? 60.0 : 0.0) + (wflow ? 8.0 : 0.0));
-            if (gauss)
+            if (fast6) {
+                if (gauss)
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, true>), gf, dim3(256), smem_fast, Ma, Mb, R0, R1,
+                               lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false>), gf, dim3(256), smem_fast, Ma, Mb, R0,
+                               R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+            } else if (gauss)
                 B2F_LAUNCH(c, CLS_ITER, bytes, k_farn_iter<true>, gi, dim3(256), smem, Ma, Mb, R0, R1, lv.fx, lv.fy, h,
                            w, khalf, box_inv, win_taps, upd, wflow);
             else

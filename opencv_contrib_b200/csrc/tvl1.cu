@@ -383,7 +383,7 @@ cudaError_t Tvl1Engine::ensure_workspace(int rows, int cols) {
     free(tma_maps_);
     tma_maps_ = nullptr;
     tma_ok_ = false;
-    if (!L_.gamma) {
+    if (!L_.gamma && !getenv("B2F_DISABLE_TMA")) {
         const size_t mb = tvl1_tma_maps_bytes();
         const size_t total = (mb * 2 * L_.nscales + 63) & ~size_t(63);
         tma_maps_ = aligned_alloc(64, total);
@@ -473,7 +473,7 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
             while (done < P.iterations) {
                 const int kk = tvl1_blocked_pick_k(knobs.fused_iters, P.iterations - done, rows, cols);
                 if (use_tma)
-                    tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
+                    tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path != 3);
                 else
                     tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);
                 cur ^= 1;

@@ -224,6 +224,31 @@ struct TmaMaps {
     CUtensorMap in[N_IN];
 };
 
+// TMA needs the global address of every box row 16-byte aligned, i.e. the box x-origin a multiple
+// of 4 floats, while region origins are only even (tile*tx - halo).  The box is therefore 8 columns
+// wider than the region and starts at the region origin rounded down to a multiple of 4; threads
+// pick their pixels out of the staged rows at a 0- or 2-float shift (8-byte aligned LDS.64).
+constexpr int TBOX_W = R + 8;               // staged row length (floats)
+constexpr int TPLANE_F = TBOX_W * R;        // floats per staged plane
+
+__device__ __forceinline__ void ld2x2(const float *s, float (&d)[4]) {
+    const float2 a = *reinterpret_cast<const float2 *>(s);
+    const float2 b = *reinterpret_cast<const float2 *>(s + 2);
+    d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+}
+
+// One lane of a fully converged warp (the canonical TMA-issue guard: the branch is warp-uniform).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void store_pairs(const Plane &P, int gy, int gx, const float (&v)[4], bool ok0, bool ok1,
                                             int cols) {
     float *row = P.row(gy) + gx;
@@ -237,64 +262,68 @@ __device__ __forceinline__ void store_pairs(const Plane &P, int gy, int gx, cons
     }
 }
 
+template <bool ELECT>
 __global__ void __launch_bounds__(NT, 1)
     k_tvl1_blocked_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12,
                        Plane o_p21, Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int tile,
                        int tiles_x, int ntiles) {
     extern __shared__ __align__(1024) float smem[];
     float *stage = smem;
-    float *ex = smem + N_IN * PLANE_F;
+    float *ex = smem + N_IN * TPLANE_F;
     uint64_t *bar = reinterpret_cast<uint64_t *>(ex + 4 * EX_F);
 
     const int tid = threadIdx.x;
     const int lx = tid & 15, tr = tid >> 4;
-    constexpr uint32_t kStageBytes = N_IN * PLANE_F * sizeof(float);
+    constexpr uint32_t kStageBytes = N_IN * TPLANE_F * sizeof(float);
 
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
     int t = blockIdx.x;
-    if (tid == 0 && t < ntiles) {
+    const bool issuer = ELECT ? (tid < 32 && elect_one()) : (tid == 0);
+    if (issuer && t < ntiles) {
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         mbar_expect_tx(bar, kStageBytes);
 #pragma unroll
         for (int pl = 0; pl < N_IN; ++pl)
-            tma_load_2d(stage + pl * PLANE_F, &maps.in[pl], tx * tile - halo, ty * tile - halo, bar);
+            tma_load_2d(stage + pl * TPLANE_F, &maps.in[pl], (tx * tile - halo) & ~3, ty * tile - halo, bar);
     }
     uint32_t parity = 0;
     for (; t < ntiles; t += gridDim.x) {
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         const int gx0 = tx * tile - halo, gy0 = ty * tile - halo;
+        const int shift = gx0 - (gx0 & ~3);  // 0 or 2
         mbar_wait(bar, parity);
         parity ^= 1;
 
         Regs r;
         {
-            const int o0 = (2 * tr) * R + 4 * lx, o1 = o0 + R;
-            ld4(stage + 0 * PLANE_F + o0, r.Ix[0]);  ld4(stage + 0 * PLANE_F + o1, r.Ix[1]);
-            ld4(stage + 1 * PLANE_F + o0, r.Iy[0]);  ld4(stage + 1 * PLANE_F + o1, r.Iy[1]);
-            ld4(stage + 2 * PLANE_F + o0, r.gr[0]);  ld4(stage + 2 * PLANE_F + o1, r.gr[1]);
-            ld4(stage + 3 * PLANE_F + o0, r.rc[0]);  ld4(stage + 3 * PLANE_F + o1, r.rc[1]);
-            ld4(stage + 4 * PLANE_F + o0, r.u1[0]);  ld4(stage + 4 * PLANE_F + o1, r.u1[1]);
-            ld4(stage + 5 * PLANE_F + o0, r.u2[0]);  ld4(stage + 5 * PLANE_F + o1, r.u2[1]);
-            ld4(stage + 6 * PLANE_F + o0, r.p11[0]); ld4(stage + 6 * PLANE_F + o1, r.p11[1]);
-            ld4(stage + 7 * PLANE_F + o0, r.p12[0]); ld4(stage + 7 * PLANE_F + o1, r.p12[1]);
-            ld4(stage + 8 * PLANE_F + o0, r.p21[0]); ld4(stage + 8 * PLANE_F + o1, r.p21[1]);
-            ld4(stage + 9 * PLANE_F + o0, r.p22[0]); ld4(stage + 9 * PLANE_F + o1, r.p22[1]);
+            const int o0 = (2 * tr) * TBOX_W + shift + 4 * lx, o1 = o0 + TBOX_W;
+            ld2x2(stage + 0 * TPLANE_F + o0, r.Ix[0]);  ld2x2(stage + 0 * TPLANE_F + o1, r.Ix[1]);
+            ld2x2(stage + 1 * TPLANE_F + o0, r.Iy[0]);  ld2x2(stage + 1 * TPLANE_F + o1, r.Iy[1]);
+            ld2x2(stage + 2 * TPLANE_F + o0, r.gr[0]);  ld2x2(stage + 2 * TPLANE_F + o1, r.gr[1]);
+            ld2x2(stage + 3 * TPLANE_F + o0, r.rc[0]);  ld2x2(stage + 3 * TPLANE_F + o1, r.rc[1]);
+            ld2x2(stage + 4 * TPLANE_F + o0, r.u1[0]);  ld2x2(stage + 4 * TPLANE_F + o1, r.u1[1]);
+            ld2x2(stage + 5 * TPLANE_F + o0, r.u2[0]);  ld2x2(stage + 5 * TPLANE_F + o1, r.u2[1]);
+            ld2x2(stage + 6 * TPLANE_F + o0, r.p11[0]); ld2x2(stage + 6 * TPLANE_F + o1, r.p11[1]);
+            ld2x2(stage + 7 * TPLANE_F + o0, r.p12[0]); ld2x2(stage + 7 * TPLANE_F + o1, r.p12[1]);
+            ld2x2(stage + 8 * TPLANE_F + o0, r.p21[0]); ld2x2(stage + 8 * TPLANE_F + o1, r.p21[1]);
+            ld2x2(stage + 9 * TPLANE_F + o0, r.p22[0]); ld2x2(stage + 9 * TPLANE_F + o1, r.p22[1]);
         }
         __syncthreads();  // the staging buffer is free again
 
         const int tn = t + gridDim.x;
-        if (tid == 0 && tn < ntiles) {
+        if (issuer && tn < ntiles) {
             const int ny = tn / tiles_x, nx = tn - ny * tiles_x;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar, kStageBytes);
 #pragma unroll
             for (int pl = 0; pl < N_IN; ++pl)
-                tma_load_2d(stage + pl * PLANE_F, &maps.in[pl], nx * tile - halo, ny * tile - halo, bar);
+                tma_load_2d(stage + pl * TPLANE_F, &maps.in[pl], (nx * tile - halo) & ~3, ny * tile - halo, bar);
         }
 
         const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
@@ -351,7 +380,7 @@ static bool encode_plane(CUtensorMap *m, const Plane &P, int rows, int cols) {
     if (!enc) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)P.pitch * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)R, (cuuint32_t)R};
+    const cuuint32_t box[2] = {(cuuint32_t)TBOX_W, (cuuint32_t)R};
     const cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, P.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -369,10 +398,10 @@ bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int row
     return true;
 }
 
-constexpr size_t SMEM_TMA_BYTES = sizeof(float) * (size_t)(N_IN * PLANE_F + 4 * EX_F) + 64;
+constexpr size_t SMEM_TMA_BYTES = sizeof(float) * (size_t)(N_IN * TPLANE_F + 4 * EX_F) + 64;
 
 void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
-                     const Tvl1Scalars &k, int iters, int num_sms) {
+                     const Tvl1Scalars &k, int iters, int num_sms, bool elect) {
     const Tvl1State &so = B.s[cur ^ 1];
     const int halo = (iters + 1) & ~1;  // even halo >= iters keeps every store 8-byte aligned
     const int tile = R - 2 * halo;
@@ -380,9 +409,14 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
     const int ntiles = tiles_x * tiles_y;
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     const double bytes = 64.0 * (double)rows * cols * iters;
-    B2F_LAUNCH(c, cls, bytes, k_tvl1_blocked_tma, dim3(grid), dim3(NT), SMEM_TMA_BYTES,
-               *static_cast<const TmaMaps *>(maps), so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
-               halo, tile, tiles_x, ntiles);
+    if (elect)
+        B2F_LAUNCH(c, cls, bytes, k_tvl1_blocked_tma<true>, dim3(grid), dim3(NT), SMEM_TMA_BYTES,
+                   *static_cast<const TmaMaps *>(maps), so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k,
+                   iters, halo, tile, tiles_x, ntiles);
+    else
+        B2F_LAUNCH(c, cls, bytes, k_tvl1_blocked_tma<false>, dim3(grid), dim3(NT), SMEM_TMA_BYTES,
+                   *static_cast<const TmaMaps *>(maps), so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k,
+                   iters, halo, tile, tiles_x, ntiles);
 }
 
 namespace {
@@ -396,7 +430,10 @@ cudaError_t tvl1_blocked_init() {
     if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
     e = cudaFuncSetAttribute(k_tvl1_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_tvl1_blocked_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)SMEM_TMA_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)SMEM_TMA_BYTES);
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;

@@ -49,6 +49,6 @@ void tvl1_blocked_launch(Ctx &c, int cls, const Tvl1BlockedPlanes &B, int cur, i
 size_t tvl1_tma_maps_bytes();
 bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int rows, int cols);
 void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
-                     const Tvl1Scalars &k, int iters, int num_sms);
+                     const Tvl1Scalars &k, int iters, int num_sms, bool elect = true);
 
 }  // namespace b2f

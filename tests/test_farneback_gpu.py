@@ -65,6 +65,22 @@ def test_engine_matches_cuda_semantics_model(cuda_device, kw):
     assert st["mean"] <= 1e-3 and st["p95"] <= 5e-3, st
 
 
+def test_register_blocked_iteration_matches_generic_kernel(cuda_device):
+    """kernel_path=1 forces the generic fused-iteration kernel; the K=6 register-blocked kernel
+    keeps the same summation order, so the flows agree to rounding noise."""
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(203, 277, seed=4, kind="smooth")
+    d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
+    for flags in (0, 256):
+        outs = []
+        for path in (0, 1):
+            alg = ocb.FarnebackOpticalFlow_create(flags=flags)
+            alg.setEngineOption("kernel_path", path)
+            outs.append(alg.calc(d0, d1).cpu().numpy())
+        assert float(np.abs(outs[0] - outs[1]).max()) <= 1e-4, flags
+
+
 def test_golden_fixtures(cuda_device):
     names = sorted(n for n in os.listdir(GOLD) if n.startswith("farneback_") and n.endswith(".npz"))
     assert names, "golden fixtures missing"

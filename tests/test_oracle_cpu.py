@@ -115,3 +115,36 @@ def test_golden_fixtures_pin_the_oracles():
         assert metrics.ncc_dissimilarity(live, z["flow"]) <= 1e-6, n
         model = fm.calc(z["I0"], z["I1"], fm.FarnebackParams(**kw))
         assert metrics.ncc_dissimilarity(model, z["flow"]) <= float(z["ncc_tol"]), n
+
+
+@pytest.fixture(scope="module")
+def native():
+    import subprocess, os
+    from oracle import tvl1_cpu_native as nat
+    if not nat.available():
+        subprocess.run(["make", "-C", os.path.dirname(nat.__file__)], check=True)
+    return nat
+
+
+def test_native_port_primitives_pinned_to_cv2(native):
+    """oracle/tvl1_cpu.c restates cv::resize(INTER_LINEAR) and cv::remap(INTER_CUBIC); pin both
+    against the live cv2 functions (the reference's own external primitives)."""
+    rng = np.random.default_rng(0)
+    a = synth.texture(211, 307, 3)
+    for (dh, dw) in [(169, 246), (264, 384), (211, 307)]:
+        r = native.resize_linear(a, dh, dw)
+        c = cv2.resize(a, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.abs(r - c).max() <= 1e-4      # <= 2 ulp at 255 (cv2 uses a fused vertical pass)
+    ys, xs = np.mgrid[0:211, 0:307].astype(np.float32)
+    mx = xs + rng.uniform(-9, 9, xs.shape).astype(np.float32)
+    my = ys + rng.uniform(-9, 9, xs.shape).astype(np.float32)
+    assert np.array_equal(native.remap_cubic(a, mx, my), cv2.remap(a, mx, my, cv2.INTER_CUBIC))  # bit exact
+
+
+def test_native_port_agrees_with_numpy_restatement(native):
+    I0, I1, gt = synth.make_pair(120, 160, seed=0, kind="smooth")
+    P = tvl1_cpu.TVL1Params(nscales=4, warps=5, epsilon=0.0, innerIterations=1, outerIterations=30,
+                            medianFiltering=1)
+    a, b = tvl1_cpu.calc(I0, I1, P), native.calc(I0, I1, P)
+    st = metrics.epe_stats(a, b)
+    assert st["mean"] <= 0.01 and st["frac_le_0.1"] >= 0.995, st
