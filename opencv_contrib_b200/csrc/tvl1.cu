@@ -138,11 +138,11 @@ __global__ void __launch_bounds__(256) k_tvl1_estimate_u(Tvl1Planes P, int rows,
         const float p22u = y > 0 ? P.p22.at(y - 1, x) : 0.f;
         float u1n, u2n;
         if (k.gamma == 0.f) {
-            tvl1_update_u(k, Ix, Iy, g, rc, u1, u2, p11, p11l, p12, p12u, p21, p21l, p22, p22u, u1n, u2n);
+            tvl1_update_u(k, Ix, Iy, tvl1_inv_grad(g), rc, u1, u2, p11, p11l, p12, p12u, p21, p21l, p22, p22u, u1n, u2n);
         } else {
             const float u3 = P.u3.at(y, x);
             const float rho = __fadd_rn(rc, __fmaf_rn(k.gamma, u3, __fmaf_rn(Iy, u2, __fmul_rn(Ix, u1))));
-            const float fi = tvl1_threshold(rho, g, k.l_t);
+            const float fi = tvl1_threshold(rho, tvl1_inv_grad(g), k.l_t);
             const float v1 = __fmaf_rn(fi, Ix, u1);
             const float v2 = __fmaf_rn(fi, Iy, u2);
             const float v3 = __fmaf_rn(fi, k.gamma, u3);
@@ -186,20 +186,15 @@ __global__ void __launch_bounds__(256) k_tvl1_estimate_dual(Tvl1Planes P, int ro
     if (x >= cols || y >= rows) return;
     const int xr = min(x + 1, cols - 1), yd = min(y + 1, rows - 1);
     {
-        const float c = P.u1.at(y, x);
-        const float ux = __fsub_rn(P.u1.at(y, xr), c), uy = __fsub_rn(P.u1.at(yd, x), c);
-        float pa = P.p11.at(y, x), pb = P.p12.at(y, x);
-        tvl1_update_p(k.taut, ux, uy, pa, pb);
-        P.p11.at(y, x) = pa;
-        P.p12.at(y, x) = pb;
-    }
-    {
-        const float c = P.u2.at(y, x);
-        const float ux = __fsub_rn(P.u2.at(y, xr), c), uy = __fsub_rn(P.u2.at(yd, x), c);
-        float pa = P.p21.at(y, x), pb = P.p22.at(y, x);
-        tvl1_update_p(k.taut, ux, uy, pa, pb);
-        P.p21.at(y, x) = pa;
-        P.p22.at(y, x) = pb;
+        const float c1 = P.u1.at(y, x), c2 = P.u2.at(y, x);
+        const float ux1 = __fsub_rn(P.u1.at(y, xr), c1), uy1 = __fsub_rn(P.u1.at(yd, x), c1);
+        const float ux2 = __fsub_rn(P.u2.at(y, xr), c2), uy2 = __fsub_rn(P.u2.at(yd, x), c2);
+        float p11 = P.p11.at(y, x), p12 = P.p12.at(y, x), p21 = P.p21.at(y, x), p22 = P.p22.at(y, x);
+        tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, p11, p12, p21, p22);
+        P.p11.at(y, x) = p11;
+        P.p12.at(y, x) = p12;
+        P.p21.at(y, x) = p21;
+        P.p22.at(y, x) = p22;
     }
     if (k.gamma != 0.f) {
         const float c = P.u3.at(y, x);

@@ -38,6 +38,12 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, cons
     const int up = max(tr - 1, 0) * R + 4 * lx;
     const int dn = min(tr + 1, 31) * R + 4 * lx;
 
+    // |grad I|^2 is constant over the iterations: turn it into the thresholding constant once
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
+
     // publish the bottom rows of p12/p22 for the first primal update
     st4(ex_p12 + mine, r.p12[1]);
     st4(ex_p22 + mine, r.p22[1]);
@@ -94,8 +100,7 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, cons
                     if (gxb + i == W - 1) { ux1 = 0.f; ux2 = 0.f; }
                     if (gyb + j == H - 1) { uy1 = 0.f; uy2 = 0.f; }
                 }
-                tvl1_update_p(k.taut, ux1, uy1, r.p11[j][i], r.p12[j][i]);
-                tvl1_update_p(k.taut, ux2, uy2, r.p21[j][i], r.p22[j][i]);
+                tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, r.p11[j][i], r.p12[j][i], r.p21[j][i], r.p22[j][i]);
             }
         }
         st4(ex_p12 + mine, r.p12[1]);

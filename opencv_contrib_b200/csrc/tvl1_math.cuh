@@ -5,9 +5,10 @@
 //   estimateUKernel             modules/cudaoptflow/src/cuda/tvl1flow.cu:209-288
 //   estimateDualVariablesKernel modules/cudaoptflow/src/cuda/tvl1flow.cu:313-348
 // Deliberate arithmetic choices (documented in DESIGN.md, covered by the tolerance tests):
-//   * -rho/grad is -rho * rcp.approx(grad) (MUFU.RCP, <= 2 ulp) instead of an IEEE divide;
-//   * hypotf(a,b) is sqrt.approx(a*a + b*b) and the dual normalisation multiplies by
-//     rcp.approx(1 + taut*g) instead of two IEEE divides;
+//   * -rho/grad is -rho * rcp.approx(grad) (MUFU.RCP, <= 2 ulp) instead of an IEEE divide, and the
+//     three-way threshold test is written as the equivalent clamp (see tvl1_threshold);
+//   * hypotf(a,b) is sqrt.approx(a*a + b*b) and the dual normalisation multiplies by a shared
+//     rcp.approx instead of IEEE divides (see tvl1_update_p2);
 //   * the divergence at the first row/column uses a zero ghost value, (p - 0) + (q - q_up), where
 //     the reference writes p + q - q_up: same value up to one rounding on that column only.
 #pragma once
@@ -24,25 +25,26 @@ struct Tvl1Scalars {
 
 #ifdef __CUDACC__
 
-// Thresholding step TH: returns the multiplier fi such that d = fi * (Ix, Iy, gamma).
-// Branch-free (selects only): a per-pixel divergent branch around the reciprocal serialises the
-// eight pixels a thread owns in the blocked kernel.
-__device__ __forceinline__ float tvl1_threshold(float rho, float grad, float l_t) {
-    const float lg = __fmul_rn(l_t, grad);
-    const float q = __fmul_rn(-rho, rcp_approx(grad));  // garbage when grad == 0, discarded below
-    float fi = grad > FLT_EPSILON ? q : 0.f;
-    fi = rho > lg ? -l_t : fi;
-    fi = rho < -lg ? l_t : fi;
-    return fi;
+// Per-pixel constant of the thresholding step: 1/|grad I|^2, or a huge value where the reference
+// treats the gradient as zero (grad <= FLT_EPSILON), so that the clamp below degenerates to the
+// reference's sign test there.  Constant over the inner iterations of a warp: the blocked kernel
+// evaluates it once per tile.
+__device__ __forceinline__ float tvl1_inv_grad(float grad) { return grad > FLT_EPSILON ? rcp_approx(grad) : 1e30f; }
+
+// Thresholding step TH (tvl1flow.cu:236-262): the multiplier fi with d = fi * (Ix, Iy, gamma).
+// The reference's three-way test  rho < -l_t*g -> l_t ; rho > l_t*g -> -l_t ; else -rho/g  is the
+// clamp of -rho/g to [-l_t, l_t] (TH is continuous in rho), evaluated branch-free with two FMNMX.
+__device__ __forceinline__ float tvl1_threshold(float rho, float inv_grad, float l_t) {
+    return fminf(fmaxf(__fmul_rn(-rho, inv_grad), -l_t), l_t);
 }
 
 // One primal update for a single pixel.  pl = p11(x-1) (0 at x==0), pu = p12(y-1) (0 at y==0).
-__device__ __forceinline__ void tvl1_update_u(const Tvl1Scalars &k, float Ix, float Iy, float grad, float rho_c,
+__device__ __forceinline__ void tvl1_update_u(const Tvl1Scalars &k, float Ix, float Iy, float inv_grad, float rho_c,
                                               float u1, float u2, float p11, float p11_l, float p12, float p12_u,
                                               float p21, float p21_l, float p22, float p22_u, float &u1n,
                                               float &u2n) {
     const float rho = __fadd_rn(rho_c, __fmaf_rn(Iy, u2, __fmul_rn(Ix, u1)));
-    const float fi = tvl1_threshold(rho, grad, k.l_t);
+    const float fi = tvl1_threshold(rho, inv_grad, k.l_t);
     const float v1 = __fmaf_rn(fi, Ix, u1);
     const float v2 = __fmaf_rn(fi, Iy, u2);
     const float div1 = __fadd_rn(__fsub_rn(p11, p11_l), __fsub_rn(p12, p12_u));
@@ -51,8 +53,25 @@ __device__ __forceinline__ void tvl1_update_u(const Tvl1Scalars &k, float Ix, fl
     u2n = __fmaf_rn(k.theta, div2, v2);
 }
 
-// One dual update for one flow component.  ux, uy are the forward differences (0 on the last
-// column / row).
+// Dual update of both flow components of one pixel (estimateDualVariablesKernel, tvl1flow.cu:313-348).
+// ux*, uy* are the forward differences (0 on the last column / row).  The two normalisations
+// 1/(1 + taut*g1), 1/(1 + taut*g2) share ONE reciprocal: r = 1/(a1*a2), inv1 = r*a2, inv2 = r*a1
+// (a1, a2 >= 1), which keeps the SFU (16 lanes/SM on B200) off the critical path.
+__device__ __forceinline__ void tvl1_update_p2(float taut, float ux1, float uy1, float ux2, float uy2, float &p11,
+                                               float &p12, float &p21, float &p22) {
+    const float g1 = sqrt_approx(__fmaf_rn(ux1, ux1, __fmul_rn(uy1, uy1)));
+    const float g2 = sqrt_approx(__fmaf_rn(ux2, ux2, __fmul_rn(uy2, uy2)));
+    const float a1 = __fmaf_rn(taut, g1, 1.0f);
+    const float a2 = __fmaf_rn(taut, g2, 1.0f);
+    const float r = rcp_approx(__fmul_rn(a1, a2));
+    const float inv1 = __fmul_rn(r, a2), inv2 = __fmul_rn(r, a1);
+    p11 = __fmul_rn(__fmaf_rn(taut, ux1, p11), inv1);
+    p12 = __fmul_rn(__fmaf_rn(taut, uy1, p12), inv1);
+    p21 = __fmul_rn(__fmaf_rn(taut, ux2, p21), inv2);
+    p22 = __fmul_rn(__fmaf_rn(taut, uy2, p22), inv2);
+}
+
+// Single-component dual update (third, illumination component when gamma != 0).
 __device__ __forceinline__ void tvl1_update_p(float taut, float ux, float uy, float &pa, float &pb) {
     const float g = sqrt_approx(__fmaf_rn(ux, ux, __fmul_rn(uy, uy)));
     const float inv = rcp_approx(__fmaf_rn(taut, g, 1.0f));
