@@ -339,6 +339,91 @@ __device__ __forceinline__ void farn_update_matrices_px(const Stack5 &R0, const 
     m[4] = r6 * r2 + r5 * r3;
 }
 
+
+// updateMatrices for 4 horizontally adjacent pixels (x multiple of 4), arranged plane-major so that the
+// 16 bilinear-gather loads of one R1 plane are all in flight together (the per-pixel form exposes one
+// L2 round trip per pixel).  Same arithmetic per pixel as farn_update_matrices_px.
+__device__ __forceinline__ void farn_update_matrices_quad(const Stack5 &R0, const Stack5 &R1, int rows, int cols,
+                                                          int x, int y, const float (&dx)[4], const float (&dy)[4],
+                                                          float (&m)[4][5]) {
+    float a00[4], a01[4], a10[4], a11[4];
+    const float *base[4];
+    bool inb[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float fx = (x + e) + dx[e], fy = y + dy[e];
+        const float ffx = fminf(fmaxf(floorf(fx), -4.f), (float)cols + 4.f);
+        const float ffy = fminf(fmaxf(floorf(fy), -4.f), (float)rows + 4.f);
+        const int x1 = (int)ffx, y1 = (int)ffy;
+        fx -= floorf(fx);
+        fy -= floorf(fy);
+        inb[e] = x1 >= 0 && y1 >= 0 && x1 < cols - 1 && y1 < rows - 1 && x + e < cols;
+        a00[e] = (1.f - fx) * (1.f - fy);
+        a01[e] = fx * (1.f - fy);
+        a10[e] = (1.f - fx) * fy;
+        a11[e] = fx * fy;
+        base[e] = &R1.at(0, inb[e] ? y1 : 0, inb[e] ? x1 : 0);
+    }
+    const size_t ps = (size_t)R1.h * R1.pitch;
+    const int pitch = R1.pitch;
+    float g[5][4];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float t00[4], t01[4], t10[4], t11[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float *p = base[e] + k * ps;
+            t00[e] = __ldg(p);
+            t01[e] = __ldg(p + 1);
+            t10[e] = __ldg(p + pitch);
+            t11[e] = __ldg(p + pitch + 1);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g[k][e] = a00[e] * t00[e] + a01[e] * t01[e] + a10[e] * t10[e] + a11[e] * t11[e];
+    }
+    float r0v[5][4];
+    const bool full = x + 3 < cols;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (full) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(&R0.at(k, y, x)));
+            r0v[k][0] = t.x; r0v[k][1] = t.y; r0v[k][2] = t.z; r0v[k][3] = t.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r0v[k][e] = x + e < cols ? __ldg(&R0.at(k, y, x + e)) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float r2, r3, r4, r5, r6;
+        if (inb[e]) {
+            r2 = g[0][e];
+            r3 = g[1][e];
+            r4 = (r0v[2][e] + g[2][e]) * 0.5f;
+            r5 = (r0v[3][e] + g[3][e]) * 0.5f;
+            r6 = (r0v[4][e] + g[4][e]) * 0.25f;
+        } else {
+            r2 = r3 = 0.f;
+            r4 = r0v[2][e];
+            r5 = r0v[3][e];
+            r6 = r0v[4][e] * 0.5f;
+        }
+        r2 = (r0v[0][e] - r2) * 0.5f;
+        r3 = (r0v[1][e] - r3) * 0.5f;
+        r2 += r4 * dy[e] + r6 * dx[e];
+        r3 += r6 * dy[e] + r5 * dx[e];
+        const int xe = x + e;
+        const float scale = farn_border_w(min(xe, BORDER_SIZE)) * farn_border_w(min(y, BORDER_SIZE)) *
+                            farn_border_w(min(cols - xe - 1, BORDER_SIZE)) * farn_border_w(min(rows - y - 1, BORDER_SIZE));
+        r2 *= scale; r3 *= scale; r4 *= scale; r5 *= scale; r6 *= scale;
+        m[e][0] = r4 * r4 + r6 * r6;
+        m[e][1] = (r4 + r5) * r6;
+        m[e][2] = r5 * r5 + r6 * r6;
+        m[e][3] = r4 * r2 + r6 * r3;
+        m[e][4] = r6 * r2 + r5 * r3;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_farn_update_matrices(Plane flowx, Plane flowy, Stack5 R0, Stack5 R1, Stack5 M,
                                                               int rows, int cols) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,7 +526,7 @@ __global__ void __launch_bounds__(256) k_farn_iter(Stack5 Min, Stack5 Mout, Stac
 // ------------------------------------------------------------------------------------------
 constexpr int FT_W = 64, FT_H = 32;
 
-template <int K, bool GAUSS>
+template <int K, bool GAUSS, bool QUAD>
 __global__ void __launch_bounds__(256) k_farn_iter_fast(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
                                                         Plane flowy, int rows, int cols, float box_inv,
                                                         const float *__restrict__ g, int update_matrices,
@@ -533,10 +618,14 @@ __global__ void __launch_bounds__(256) k_farn_iter_fast(Stack5 Min, Stack5 Mout,
         }
         if (update_matrices) {
             float m[4][5];
+            if (QUAD) {
+                farn_update_matrices_quad(R0, R1, rows, cols, x, y, fx, fy, m);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (x + e < cols) farn_update_matrices_px(R0, R1, rows, cols, x + e, y, fx[e], fy[e], m[e]);
-                else { m[e][0] = m[e][1] = m[e][2] = m[e][3] = m[e][4] = 0.f; }
+                for (int e = 0; e < 4; ++e) {
+                    if (x + e < cols) farn_update_matrices_px(R0, R1, rows, cols, x + e, y, fx[e], fy[e], m[e]);
+                    else { m[e][0] = m[e][1] = m[e][2] = m[e][3] = m[e][4] = 0.f; }
+                }
             }
 #pragma unroll
             for (int pl = 0; pl < 5; ++pl) {
@@ -720,8 +809,10 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
         cudaGetDevice(&dev);
         if (dev >= 0 && dev < 64 && !attr_done[dev]) {
             const int bytes = (int)(sizeof(float) * 5 * FT_H * (FT_W + 12));
-            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             attr_done[dev] = c.ok();
         }
     }
@@ -812,12 +903,19 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
             const int wflow = !upd;
             const double bytes = npx * (20.0 + (upd ? 60.0 : 0.0) + (wflow ? 8.0 : 0.0));
             if (fast6) {
-                if (gauss)
-                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, true>), gf, dim3(256), smem_fast, Ma, Mb, R0, R1,
-                               lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
-                else
-                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false>), gf, dim3(256), smem_fast, Ma, Mb, R0,
+                const bool quad = knobs.kernel_path != 2;
+                if (gauss && quad)
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, true, true>), gf, dim3(256), smem_fast, Ma, Mb, R0,
                                R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else if (gauss)
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, true, false>), gf, dim3(256), smem_fast, Ma, Mb, R0,
+                               R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else if (quad)
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true>), gf, dim3(256), smem_fast, Ma, Mb, R0,
+                               R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, false>), gf, dim3(256), smem_fast, Ma, Mb,
+                               R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
             } else if (gauss)
                 B2F_LAUNCH(c, CLS_ITER, bytes, k_farn_iter<true>, gi, dim3(256), smem, Ma, Mb, R0, R1, lv.fx, lv.fy, h,
                            w, khalf, box_inv, win_taps, upd, wflow);

@@ -13,7 +13,7 @@ constexpr int PLANE_F = R * R;            // floats per staged plane
 constexpr int N_IN = 10;                  // Ix, Iy, grad, rho_c, u1, u2, p11, p12, p21, p22
 constexpr int N_OUT = 6;                  // u1, u2, p11, p12, p21, p22
 constexpr int EX_F = 32 * R;              // floats per exchange array (32 thread-rows x 64)
-constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(N_IN * PLANE_F + 4 * EX_F) + 64;
+constexpr size_t SMEM_BYTES = sizeof(float) * (size_t)(N_IN * PLANE_F + 4 * EX_F);
 
 struct Regs {
     float Ix[2][4], Iy[2][4], gr[2][4], rc[2][4];
@@ -28,96 +28,13 @@ __device__ __forceinline__ void st4(float *s, const float (&d)[4]) {
     *reinterpret_cast<float4 *>(s) = make_float4(d[0], d[1], d[2], d[3]);
 }
 
-// ---- mbarrier helpers (split-phase CTA barriers and TMA completion) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// One arrival per warp (the barriers are initialised with count = warps per CTA): __syncwarp orders the
-// warp's shared-memory stores before lane 0's release-arrive.
-__device__ __forceinline__ void warp_arrive(uint64_t *bar) {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0)
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-struct IterSync {
-    uint64_t *bar_u, *bar_p;  // "new u rows published", "new p rows published"
-    uint32_t par_u, par_p;    // running phase parities (persist across tiles)
-};
-
-template <bool BORDER, int J>
-__device__ __forceinline__ void primal_row(Regs &r, const Tvl1Scalars &k, const float (&up12)[4],
-                                           const float (&up22)[4], int gxb, int gyb) {
-    const float l11 = __shfl_up_sync(0xffffffffu, r.p11[J][3], 1, 16);
-    const float l21 = __shfl_up_sync(0xffffffffu, r.p21[J][3], 1, 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float pl11 = i ? r.p11[J][i ? i - 1 : 0] : l11;
-        float pl21 = i ? r.p21[J][i ? i - 1 : 0] : l21;
-        float pu12 = J ? r.p12[0][i] : up12[i];
-        float pu22 = J ? r.p22[0][i] : up22[i];
-        if (BORDER) {
-            if (gxb + i == 0) { pl11 = 0.f; pl21 = 0.f; }
-            if (gyb + J == 0) { pu12 = 0.f; pu22 = 0.f; }
-        }
-        float a, b;
-        tvl1_update_u(k, r.Ix[J][i], r.Iy[J][i], r.gr[J][i], r.rc[J][i], r.u1[J][i], r.u2[J][i], r.p11[J][i], pl11,
-                      r.p12[J][i], pu12, r.p21[J][i], pl21, r.p22[J][i], pu22, a, b);
-        r.u1[J][i] = a;
-        r.u2[J][i] = b;
-    }
-}
-
-template <bool BORDER, int J>
-__device__ __forceinline__ void dual_row(Regs &r, const Tvl1Scalars &k, const float (&dn1)[4], const float (&dn2)[4],
-                                         int gxb, int gyb, int W, int H) {
-    const float r1 = __shfl_down_sync(0xffffffffu, r.u1[J][0], 1, 16);
-    const float r2 = __shfl_down_sync(0xffffffffu, r.u2[J][0], 1, 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float c1 = r.u1[J][i], c2 = r.u2[J][i];
-        const float ur1 = i < 3 ? r.u1[J][i < 3 ? i + 1 : 3] : r1;
-        const float ur2 = i < 3 ? r.u2[J][i < 3 ? i + 1 : 3] : r2;
-        const float ud1 = J == 0 ? r.u1[1][i] : dn1[i];
-        const float ud2 = J == 0 ? r.u2[1][i] : dn2[i];
-        float ux1 = __fsub_rn(ur1, c1), uy1 = __fsub_rn(ud1, c1);
-        float ux2 = __fsub_rn(ur2, c2), uy2 = __fsub_rn(ud2, c2);
-        if (BORDER) {
-            if (gxb + i == W - 1) { ux1 = 0.f; ux2 = 0.f; }
-            if (gyb + J == H - 1) { uy1 = 0.f; uy2 = 0.f; }
-        }
-        tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, r.p11[J][i], r.p12[J][i], r.p21[J][i], r.p22[J][i]);
-    }
-}
-
 // K iterations on the register-resident region.  ex = 4 exchange arrays [u1 | u2 | p12 | p22].
 // gxb/gyb: global coordinates of the thread's first pixel; W/H image size (BORDER only).
-//
-// Cross-warp dependencies are only the rows at the edge of each thread's 4x2 micro-tile, so the
-// two CTA-wide synchronisations per iteration are SPLIT-PHASE mbarriers: a warp publishes its edge
-// row, arrives, and keeps computing the row that needs no neighbour data before it waits.  Order
-// per iteration:   primal(row 1) | wait P | primal(row 0) | publish u, arrive U |
-//                  dual(row 0)   | wait U | dual(row 1)   | publish p, arrive P
-// Buffer reuse is safe without double buffering: a warp overwrites its u (p) row only after passing
-// wait P (wait U), which every warp arrives at only after its last read of the previous u (p) rows.
+// `halo` (>= iters) is the tile inset: iteration `it` only has to update the rows within
+// (iters - 1 - it) of the centre tile -- the dependency cone of the final result -- so warps whose
+// four rows lie outside that band skip the arithmetic (they still take part in the barriers).
 template <bool BORDER>
-__device__ __forceinline__ void tile_iterate(Regs &r, float *ex, IterSync &sy, int iters, const Tvl1Scalars k, int lx,
+__device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, int halo, const Tvl1Scalars k, int lx,
                                              int tr, int gxb, int gyb, int W, int H) {
     float *ex_u1 = ex, *ex_u2 = ex + EX_F, *ex_p12 = ex + 2 * EX_F, *ex_p22 = ex + 3 * EX_F;
     const int mine = tr * R + 4 * lx;
@@ -133,35 +50,74 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, IterSync &sy, i
     // publish the bottom rows of p12/p22 for the first primal update
     st4(ex_p12 + mine, r.p12[1]);
     st4(ex_p22 + mine, r.p22[1]);
-    warp_arrive(sy.bar_p);
+    __syncthreads();
 
-    const float none[4] = {0.f, 0.f, 0.f, 0.f};
+    const int wrow = (tr >> 1) << 2;  // first region row of this warp (4 rows per warp)
     for (int it = 0; it < iters; ++it) {
+        const int reach = iters - 1 - it;
+        // the primal step feeds the dual step of the row above it, hence the extra row below
+        const bool act_u = wrow + 3 >= halo - reach && wrow < R - halo + reach + 1;
+        const bool act_p = wrow + 3 >= halo - reach && wrow < R - halo + reach;
         // ---------------- primal update (estimateU) ----------------
-        primal_row<BORDER, 1>(r, k, none, none, gxb, gyb);
-        mbar_wait(sy.bar_p, sy.par_p);
-        sy.par_p ^= 1;
         float up12[4], up22[4];
         ld4(ex_p12 + up, up12);
         ld4(ex_p22 + up, up22);
-        primal_row<BORDER, 0>(r, k, up12, up22, gxb, gyb);
+        if (act_u) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float l11 = __shfl_up_sync(0xffffffffu, r.p11[j][3], 1, 16);
+            const float l21 = __shfl_up_sync(0xffffffffu, r.p21[j][3], 1, 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float pl11 = i ? r.p11[j][i ? i - 1 : 0] : l11;
+                float pl21 = i ? r.p21[j][i ? i - 1 : 0] : l21;
+                float pu12 = j ? r.p12[0][i] : up12[i];
+                float pu22 = j ? r.p22[0][i] : up22[i];
+                if (BORDER) {
+                    if (gxb + i == 0) { pl11 = 0.f; pl21 = 0.f; }
+                    if (gyb + j == 0) { pu12 = 0.f; pu22 = 0.f; }
+                }
+                float a, b;
+                tvl1_update_u(k, r.Ix[j][i], r.Iy[j][i], r.gr[j][i], r.rc[j][i], r.u1[j][i], r.u2[j][i],
+                              r.p11[j][i], pl11, r.p12[j][i], pu12, r.p21[j][i], pl21, r.p22[j][i], pu22, a, b);
+                r.u1[j][i] = a;
+                r.u2[j][i] = b;
+            }
+        }
+        }
         st4(ex_u1 + mine, r.u1[0]);
         st4(ex_u2 + mine, r.u2[0]);
-        warp_arrive(sy.bar_u);
+        __syncthreads();
 
         // ---------------- dual update (estimateDualVariables) ----------------
-        dual_row<BORDER, 0>(r, k, none, none, gxb, gyb, W, H);
-        mbar_wait(sy.bar_u, sy.par_u);
-        sy.par_u ^= 1;
         float dn1[4], dn2[4];
         ld4(ex_u1 + dn, dn1);
         ld4(ex_u2 + dn, dn2);
-        dual_row<BORDER, 1>(r, k, dn1, dn2, gxb, gyb, W, H);
-        if (it + 1 < iters) {
-            st4(ex_p12 + mine, r.p12[1]);
-            st4(ex_p22 + mine, r.p22[1]);
-            warp_arrive(sy.bar_p);
+        if (act_p) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float r1 = __shfl_down_sync(0xffffffffu, r.u1[j][0], 1, 16);
+            const float r2 = __shfl_down_sync(0xffffffffu, r.u2[j][0], 1, 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float c1 = r.u1[j][i], c2 = r.u2[j][i];
+                const float ur1 = i < 3 ? r.u1[j][i < 3 ? i + 1 : 3] : r1;
+                const float ur2 = i < 3 ? r.u2[j][i < 3 ? i + 1 : 3] : r2;
+                const float ud1 = j == 0 ? r.u1[1][i] : dn1[i];
+                const float ud2 = j == 0 ? r.u2[1][i] : dn2[i];
+                float ux1 = __fsub_rn(ur1, c1), uy1 = __fsub_rn(ud1, c1);
+                float ux2 = __fsub_rn(ur2, c2), uy2 = __fsub_rn(ud2, c2);
+                if (BORDER) {
+                    if (gxb + i == W - 1) { ux1 = 0.f; ux2 = 0.f; }
+                    if (gyb + j == H - 1) { uy1 = 0.f; uy2 = 0.f; }
+                }
+                tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, r.p11[j][i], r.p12[j][i], r.p21[j][i], r.p22[j][i]);
+            }
         }
+        }
+        st4(ex_p12 + mine, r.p12[1]);
+        st4(ex_p22 + mine, r.p22[1]);
+        __syncthreads();
     }
 }
 
@@ -178,16 +134,9 @@ __global__ void __launch_bounds__(NT, 1)
     extern __shared__ __align__(16) float smem[];
     float *stage = smem;
     float *ex = smem + N_IN * PLANE_F;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ex + 4 * EX_F);
 
     const int tid = threadIdx.x;
     const int lx = tid & 15, tr = tid >> 4;
-    if (tid == 0) {
-        mbar_init(bars + 0, NT / 32);
-        mbar_init(bars + 1, NT / 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    IterSync sy{bars + 0, bars + 1, 0u, 0u};
     const int gx0 = blockIdx.x * tile - iters;  // region origin (may be negative)
     const int gy0 = blockIdx.y * tile - iters;
 
@@ -226,9 +175,9 @@ __global__ void __launch_bounds__(NT, 1)
     const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
     const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
     if (border)
-        tile_iterate<true>(r, ex, sy, iters, k, lx, tr, gxb, gyb, cols, rows);
+        tile_iterate<true>(r, ex, iters, iters, k, lx, tr, gxb, gyb, cols, rows);
     else
-        tile_iterate<false>(r, ex, sy, iters, k, lx, tr, gxb, gyb, cols, rows);
+        tile_iterate<false>(r, ex, iters, iters, k, lx, tr, gxb, gyb, cols, rows);
 
     // ---- write the centre tile back through the staging buffer ----
     {
@@ -263,6 +212,25 @@ __global__ void __launch_bounds__(NT, 1)
 // so the HBM stream overlaps the K iterations; results leave as 8-byte vector stores straight
 // from registers (they drain while the next tile computes).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -322,13 +290,10 @@ __global__ void __launch_bounds__(NT, 1)
 
     if (tid == 0) {
         mbar_init(bar, 1);
-        mbar_init(bar + 1, NT / 32);
-        mbar_init(bar + 2, NT / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    IterSync sy{bar + 1, bar + 2, 0u, 0u};
 
     int t = blockIdx.x;
     const bool issuer = ELECT ? (tid < 32 && elect_one()) : (tid == 0);
@@ -376,9 +341,9 @@ __global__ void __launch_bounds__(NT, 1)
         const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
         const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
         if (border)
-            tile_iterate<true>(r, ex, sy, iters, k, lx, tr, gxb, gyb, cols, rows);
+            tile_iterate<true>(r, ex, iters, halo, k, lx, tr, gxb, gyb, cols, rows);
         else
-            tile_iterate<false>(r, ex, sy, iters, k, lx, tr, gxb, gyb, cols, rows);
+            tile_iterate<false>(r, ex, iters, halo, k, lx, tr, gxb, gyb, cols, rows);
 
         // centre tile -> global, 8-byte stores (halo, tile and gx0 are even, so pairs never straddle);
         // all six output planes share one pitch, so one element offset serves them all
