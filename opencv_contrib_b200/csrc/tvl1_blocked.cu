@@ -30,12 +30,9 @@ __device__ __forceinline__ void st4(float *s, const float (&d)[4]) {
 
 // K iterations on the register-resident region.  ex = 4 exchange arrays [u1 | u2 | p12 | p22].
 // gxb/gyb: global coordinates of the thread's first pixel; W/H image size (BORDER only).
-// `halo` (>= iters) is the tile inset: iteration `it` only has to update the rows within
-// (iters - 1 - it) of the centre tile -- the dependency cone of the final result -- so warps whose
-// four rows lie outside that band skip the arithmetic (they still take part in the barriers).
 template <bool BORDER>
-__device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, int halo, const Tvl1Scalars k, int lx,
-                                             int tr, int gxb, int gyb, int W, int H) {
+__device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, const Tvl1Scalars k, int lx, int tr,
+                                             int gxb, int gyb, int W, int H) {
     float *ex_u1 = ex, *ex_u2 = ex + EX_F, *ex_p12 = ex + 2 * EX_F, *ex_p22 = ex + 3 * EX_F;
     const int mine = tr * R + 4 * lx;
     const int up = max(tr - 1, 0) * R + 4 * lx;
@@ -52,17 +49,11 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, int 
     st4(ex_p22 + mine, r.p22[1]);
     __syncthreads();
 
-    const int wrow = (tr >> 1) << 2;  // first region row of this warp (4 rows per warp)
     for (int it = 0; it < iters; ++it) {
-        const int reach = iters - 1 - it;
-        // the primal step feeds the dual step of the row above it, hence the extra row below
-        const bool act_u = wrow + 3 >= halo - reach && wrow < R - halo + reach + 1;
-        const bool act_p = wrow + 3 >= halo - reach && wrow < R - halo + reach;
         // ---------------- primal update (estimateU) ----------------
         float up12[4], up22[4];
         ld4(ex_p12 + up, up12);
         ld4(ex_p22 + up, up22);
-        if (act_u) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const float l11 = __shfl_up_sync(0xffffffffu, r.p11[j][3], 1, 16);
@@ -84,7 +75,6 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, int 
                 r.u2[j][i] = b;
             }
         }
-        }
         st4(ex_u1 + mine, r.u1[0]);
         st4(ex_u2 + mine, r.u2[0]);
         __syncthreads();
@@ -93,7 +83,6 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, int 
         float dn1[4], dn2[4];
         ld4(ex_u1 + dn, dn1);
         ld4(ex_u2 + dn, dn2);
-        if (act_p) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const float r1 = __shfl_down_sync(0xffffffffu, r.u1[j][0], 1, 16);
@@ -113,7 +102,6 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, int 
                 }
                 tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, r.p11[j][i], r.p12[j][i], r.p21[j][i], r.p22[j][i]);
             }
-        }
         }
         st4(ex_p12 + mine, r.p12[1]);
         st4(ex_p22 + mine, r.p22[1]);
@@ -175,9 +163,9 @@ __global__ void __launch_bounds__(NT, 1)
     const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
     const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
     if (border)
-        tile_iterate<true>(r, ex, iters, iters, k, lx, tr, gxb, gyb, cols, rows);
+        tile_iterate<true>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
     else
-        tile_iterate<false>(r, ex, iters, iters, k, lx, tr, gxb, gyb, cols, rows);
+        tile_iterate<false>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
 
     // ---- write the centre tile back through the staging buffer ----
     {
@@ -341,9 +329,9 @@ __global__ void __launch_bounds__(NT, 1)
         const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
         const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
         if (border)
-            tile_iterate<true>(r, ex, iters, halo, k, lx, tr, gxb, gyb, cols, rows);
+            tile_iterate<true>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
         else
-            tile_iterate<false>(r, ex, iters, halo, k, lx, tr, gxb, gyb, cols, rows);
+            tile_iterate<false>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
 
         // centre tile -> global, 8-byte stores (halo, tile and gx0 are even, so pairs never straddle);
         // all six output planes share one pitch, so one element offset serves them all
@@ -458,7 +446,7 @@ cudaError_t tvl1_blocked_init() {
 int tvl1_blocked_pick_k(int knob, int remaining, int rows, int cols) {
     (void)rows;
     (void)cols;
-    int kk = knob > 0 ? knob : 6;
+    int kk = knob > 0 ? knob : 8;
     if (kk > TVL1_KMAX) kk = TVL1_KMAX;
     if (kk > remaining) kk = remaining;
     return kk;
