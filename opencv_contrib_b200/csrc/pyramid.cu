@@ -107,20 +107,21 @@ __global__ void k_pyr_down(Plane s, int srows, int scols, Plane d, int drows, in
         ry[k] = reflect101(sy - 2 + k, srows);
         rx[k] = reflect101(sx - 2 + k, scols);
     }
-    // vertical pass per column (as the reference: smem[..] = 1*r0 + 4*r1 + 6*r2 + 4*r3 + 1*r4)
+    // vertical 5-tap per source column, then horizontal 5-tap, each in the reference's left-to-right
+    // order 0.0625*a + 0.25*b + 0.375*c + 0.25*d + 0.0625*e (pyr_down.cu:68-73,139-144)
     float col[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        float sum = 0.0625f * __ldg(&s.at(ry[2], rx[i])) * 6.f;
+        float sum = 0.0625f * __ldg(&s.at(ry[0], rx[i]));
         sum = sum + 0.25f * __ldg(&s.at(ry[1], rx[i]));
-        sum = sum + 0.0625f * __ldg(&s.at(ry[0], rx[i]));
+        sum = sum + 0.375f * __ldg(&s.at(ry[2], rx[i]));
         sum = sum + 0.25f * __ldg(&s.at(ry[3], rx[i]));
         sum = sum + 0.0625f * __ldg(&s.at(ry[4], rx[i]));
         col[i] = sum;
     }
-    float out = 0.0625f * col[2] * 6.f;
+    float out = 0.0625f * col[0];
     out = out + 0.25f * col[1];
-    out = out + 0.0625f * col[0];
+    out = out + 0.375f * col[2];
     out = out + 0.25f * col[3];
     out = out + 0.0625f * col[4];
     d.at(y, x) = out;

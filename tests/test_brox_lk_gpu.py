@@ -1,0 +1,106 @@
+"""GPU tests for BroxOpticalFlow and DensePyrLKOpticalFlow (through the C ABI via ctypes).
+
+Both algorithms are *parity unpinned* upstream (no CPU implementation; Brox's golden file lives in
+opencv_extra, DensePyrLK has no accuracy test at all -- SURVEY.md §8c), so the engine is compared
+with the numpy restatements of the CUDA reference (oracle/brox_model.py, oracle/denselk_model.py),
+plus the reference's own sanity criteria: no NaN/Inf (BroxOpticalFlow.OpticalFlowNan,
+test_optflow.cpp:130-161) and recovery of a known synthetic motion.
+"""
+import numpy as np
+import pytest
+
+from oracle import synth, metrics, brox_model as bm, denselk_model as lk
+
+pytestmark = pytest.mark.gpu
+
+
+def _brox(dev, I0, I1, graph=1, **kw):
+    import torch
+    import opencv_contrib_b200 as ocb
+    alg = ocb.BroxOpticalFlow_create(**kw)
+    alg.setEngineOption("use_graph", graph)
+    f = alg.calc(torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev))
+    torch.cuda.synchronize()
+    return f.cpu().numpy(), alg
+
+
+@pytest.mark.parametrize("h,w,kind", [(96, 128, "const"), (121, 163, "smooth")])
+def test_brox_matches_model(cuda_device, h, w, kind):
+    I0, I1, gt = synth.make_pair(h, w, seed=3, kind=kind, dtype="f32")
+    kw = dict(alpha=0.197, gamma=50.0, scale_factor=0.8, inner_iterations=5, outer_iterations=77, solver_iterations=5)
+    ref = bm.calc(I0, I1, bm.BroxParams(**kw))
+    for graph in (0, 1):
+        got, alg = _brox(cuda_device, I0, I1, graph=graph, **kw)
+        assert np.isfinite(got).all()
+        st = metrics.epe_stats(got, ref)
+        assert st["mean"] <= 2e-3 and st["p95"] <= 1e-2, (graph, st)
+    assert alg.getStats()["levels"] == len(bm.pyramid_sizes(h, w, 0.8, 77))
+    assert alg.getDefaultName() == "DenseOpticalFlow.BroxOpticalFlow"
+
+
+def test_brox_reference_test_parameters_recover_motion(cuda_device):
+    # the only parameter set the reference ever runs: create(0.197, 50, 0.8, 10, 77, 10) (test_optflow.cpp:75-76)
+    I0, I1, gt = synth.make_pair(240, 320, seed=1, kind="const", dtype="f32")
+    got, _ = _brox(cuda_device, I0, I1, alpha=0.197, gamma=50.0, scale_factor=0.8, inner_iterations=10,
+                   outer_iterations=77, solver_iterations=10)
+    assert np.isfinite(got).all()                        # OpticalFlowNan criterion
+    c = got[24:-24, 24:-24]
+    assert abs(float(np.median(c[..., 0])) - 2.5) < 0.15 and abs(float(np.median(c[..., 1])) + 1.25) < 0.15
+    again, _ = _brox(cuda_device, I0, I1, alpha=0.197, gamma=50.0, scale_factor=0.8, inner_iterations=10,
+                     outer_iterations=77, solver_iterations=10)
+    assert np.array_equal(again, got)                    # deterministic
+
+
+def test_brox_error_codes(cuda_device):
+    import torch
+    import opencv_contrib_b200 as ocb
+    a = torch.zeros((64, 64), dtype=torch.uint8, device=cuda_device)
+    alg = ocb.BroxOpticalFlow_create()
+    with pytest.raises(ocb.B2FError) as e:
+        alg.calc(a, a)
+    assert e.value.status == 2                           # CV_32FC1 only (brox.cpp:134)
+    alg = ocb.BroxOpticalFlow_create(alpha=0.0)
+    with pytest.raises(ocb.B2FError) as e:
+        alg.calc(a.float(), a.float())
+    assert e.value.status == 1                           # "Invalid alpha" (NCVBroxOpticalFlow.cu:606)
+
+
+def _lk(dev, I0, I1, **kw):
+    import torch
+    import opencv_contrib_b200 as ocb
+    alg = ocb.DensePyrLKOpticalFlow_create(**kw)
+    f = alg.calc(torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev))
+    torch.cuda.synchronize()
+    return f.cpu().numpy(), alg
+
+
+@pytest.mark.parametrize("win,levels,iters", [((7, 7), 2, 10), ((13, 13), 3, 30), ((5, 9), 1, 5)])
+def test_denselk_matches_model(cuda_device, win, levels, iters):
+    I0, I1, gt = synth.make_pair(72, 100, seed=5, kind="const")
+    ref = lk.calc(I0, I1, win, levels, iters)
+    got, alg = _lk(cuda_device, I0, I1, winSize=win, maxLevel=levels, iters=iters)
+    assert np.isfinite(got).all()
+    # int-truncated samples make single pixels jump when a bilinear value sits on an integer boundary;
+    # the comparison is therefore statistical
+    e = metrics.epe(got, ref)
+    assert float((e <= 1e-2).mean()) >= 0.97 and float(np.median(e)) <= 1e-4, (float((e <= 1e-2).mean()), float(e.max()))
+    assert alg.getDefaultName() == "DenseOpticalFlow.DensePyrLKOpticalFlow"
+    assert alg.getWinSize() == win and alg.getMaxLevel() == levels and alg.getNumIters() == iters
+
+
+def test_denselk_recovers_motion_and_rejects_bad_args(cuda_device):
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, gt = synth.make_pair(240, 320, seed=2, kind="const")
+    got, _ = _lk(cuda_device, I0, I1)                    # defaults 13x13, 3 levels, 30 iterations
+    c = got[32:-32, 32:-32]
+    assert abs(float(np.median(c[..., 0])) - 2.5) < 0.2 and abs(float(np.median(c[..., 1])) + 1.25) < 0.2
+    again, _ = _lk(cuda_device, I0, I1)
+    assert np.array_equal(again, got)
+    a = torch.zeros((64, 64), dtype=torch.float32, device=cuda_device)
+    with pytest.raises(ocb.B2FError) as e:
+        ocb.DensePyrLKOpticalFlow_create().calc(a, a)
+    assert e.value.status == 2                           # CV_8UC1 only (pyrlk.cpp:240)
+    with pytest.raises(ocb.B2FError) as e:
+        ocb.DensePyrLKOpticalFlow_create(winSize=(2, 13)).calc(a.to(torch.uint8), a.to(torch.uint8))
+    assert e.value.status == 1                           # winSize > 2 (pyrlk.cpp:243)
