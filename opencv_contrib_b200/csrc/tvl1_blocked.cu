@@ -233,8 +233,9 @@ struct TmaMaps {
 // of 4 floats, while region origins are only even (tile*tx - halo).  The box is therefore 8 columns
 // wider than the region and starts at the region origin rounded down to a multiple of 4; threads
 // pick their pixels out of the staged rows at a 0- or 2-float shift (8-byte aligned LDS.64).
-constexpr int TBOX_W = R + 8;               // staged row length (floats)
-constexpr int TPLANE_F = TBOX_W * R;        // floats per staged plane
+// When the region origin is itself a multiple of 4 (halo and tile multiples of 4, e.g. K = 8) the box
+// is exactly the region (BOXW = 64) and threads read their pixels with conflict-free LDS.128.
+constexpr int TBOX_WIDE = R + 8;            // staged row length (floats), unaligned origins
 
 __device__ __forceinline__ void ld2x2(const float *s, float (&d)[4]) {
     const float2 a = *reinterpret_cast<const float2 *>(s);
@@ -262,11 +263,12 @@ __device__ __forceinline__ void store_pairs(float *p, const float (&v)[4], int m
     else if (m1 == 1) p[2] = v[2];
 }
 
-template <bool ELECT>
+template <bool ELECT, int TBOX_W>
 __global__ void __launch_bounds__(NT, 1)
     k_tvl1_blocked_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12,
                        Plane o_p21, Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int tile,
                        int tiles_x, int ntiles) {
+    constexpr int TPLANE_F = TBOX_W * R;  // floats per staged plane
     extern __shared__ __align__(1024) float smem[];
     float *stage = smem;
     float *ex = smem + N_IN * TPLANE_F;
@@ -303,16 +305,25 @@ __global__ void __launch_bounds__(NT, 1)
         Regs r;
         {
             const int o0 = (2 * tr) * TBOX_W + shift + 4 * lx, o1 = o0 + TBOX_W;
-            ld2x2(stage + 0 * TPLANE_F + o0, r.Ix[0]);  ld2x2(stage + 0 * TPLANE_F + o1, r.Ix[1]);
-            ld2x2(stage + 1 * TPLANE_F + o0, r.Iy[0]);  ld2x2(stage + 1 * TPLANE_F + o1, r.Iy[1]);
-            ld2x2(stage + 2 * TPLANE_F + o0, r.gr[0]);  ld2x2(stage + 2 * TPLANE_F + o1, r.gr[1]);
-            ld2x2(stage + 3 * TPLANE_F + o0, r.rc[0]);  ld2x2(stage + 3 * TPLANE_F + o1, r.rc[1]);
-            ld2x2(stage + 4 * TPLANE_F + o0, r.u1[0]);  ld2x2(stage + 4 * TPLANE_F + o1, r.u1[1]);
-            ld2x2(stage + 5 * TPLANE_F + o0, r.u2[0]);  ld2x2(stage + 5 * TPLANE_F + o1, r.u2[1]);
-            ld2x2(stage + 6 * TPLANE_F + o0, r.p11[0]); ld2x2(stage + 6 * TPLANE_F + o1, r.p11[1]);
-            ld2x2(stage + 7 * TPLANE_F + o0, r.p12[0]); ld2x2(stage + 7 * TPLANE_F + o1, r.p12[1]);
-            ld2x2(stage + 8 * TPLANE_F + o0, r.p21[0]); ld2x2(stage + 8 * TPLANE_F + o1, r.p21[1]);
-            ld2x2(stage + 9 * TPLANE_F + o0, r.p22[0]); ld2x2(stage + 9 * TPLANE_F + o1, r.p22[1]);
+            auto ldrow = [&](int pl, float (&a)[4], float (&b)[4]) {
+                if (TBOX_W == R) {  // aligned origin: one 16-byte load per row
+                    ld4(stage + pl * TPLANE_F + o0, a);
+                    ld4(stage + pl * TPLANE_F + o1, b);
+                } else {
+                    ld2x2(stage + pl * TPLANE_F + o0, a);
+                    ld2x2(stage + pl * TPLANE_F + o1, b);
+                }
+            };
+            ldrow(0, r.Ix[0], r.Ix[1]);
+            ldrow(1, r.Iy[0], r.Iy[1]);
+            ldrow(2, r.gr[0], r.gr[1]);
+            ldrow(3, r.rc[0], r.rc[1]);
+            ldrow(4, r.u1[0], r.u1[1]);
+            ldrow(5, r.u2[0], r.u2[1]);
+            ldrow(6, r.p11[0], r.p11[1]);
+            ldrow(7, r.p12[0], r.p12[1]);
+            ldrow(8, r.p21[0], r.p21[1]);
+            ldrow(9, r.p22[0], r.p22[1]);
         }
         __syncthreads();  // the staging buffer is free again
 
@@ -379,30 +390,33 @@ static EncodeTiledFn get_encoder() {
     return fn;
 }
 
-static bool encode_plane(CUtensorMap *m, const Plane &P, int rows, int cols) {
+static bool encode_plane(CUtensorMap *m, const Plane &P, int rows, int cols, int box_w) {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)P.pitch * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)TBOX_W, (cuuint32_t)R};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)R};
     const cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, P.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-size_t tvl1_tma_maps_bytes() { return sizeof(TmaMaps); }
+// one block = two descriptor sets: [0] 72-wide boxes (any even origin), [1] 64-wide boxes (origin % 4 == 0)
+size_t tvl1_tma_maps_bytes() { return 2 * sizeof(TmaMaps); }
 
 bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int rows, int cols) {
     TmaMaps *m = static_cast<TmaMaps *>(dst);
     const Tvl1State &si = B.s[cur];
     const Plane in[N_IN] = {B.I1wx, B.I1wy, B.grad, B.rho_c, si.u1, si.u2, si.p11, si.p12, si.p21, si.p22};
-    for (int i = 0; i < N_IN; ++i)
-        if (!encode_plane(&m->in[i], in[i], rows, cols)) return false;
+    for (int i = 0; i < N_IN; ++i) {
+        if (!encode_plane(&m[0].in[i], in[i], rows, cols, TBOX_WIDE)) return false;
+        if (!encode_plane(&m[1].in[i], in[i], rows, cols, R)) return false;
+    }
     return true;
 }
 
-constexpr size_t SMEM_TMA_BYTES = sizeof(float) * (size_t)(N_IN * TPLANE_F + 4 * EX_F) + 64;
+constexpr size_t smem_tma_bytes(int box_w) { return sizeof(float) * (size_t)(N_IN * box_w * R + 4 * EX_F) + 64; }
 
 void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                      const Tvl1Scalars &k, int iters, int num_sms, bool elect) {
@@ -413,14 +427,19 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
     const int ntiles = tiles_x * tiles_y;
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     const double bytes = 64.0 * (double)rows * cols * iters;
-    if (elect)
-        B2F_LAUNCH(c, cls, bytes, k_tvl1_blocked_tma<true>, dim3(grid), dim3(NT), SMEM_TMA_BYTES,
-                   *static_cast<const TmaMaps *>(maps), so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k,
-                   iters, halo, tile, tiles_x, ntiles);
+    const bool aligned = (halo & 3) == 0 && (tile & 3) == 0;  // every region origin is a multiple of 4
+    const TmaMaps *m = static_cast<const TmaMaps *>(maps) + (aligned ? 1 : 0);
+    if (aligned)
+        B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R>), dim3(grid), dim3(NT), smem_tma_bytes(R), *m, so.u1,
+                   so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles);
+    else if (elect)
+        B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, TBOX_WIDE>), dim3(grid), dim3(NT),
+                   smem_tma_bytes(TBOX_WIDE), *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
+                   halo, tile, tiles_x, ntiles);
     else
-        B2F_LAUNCH(c, cls, bytes, k_tvl1_blocked_tma<false>, dim3(grid), dim3(NT), SMEM_TMA_BYTES,
-                   *static_cast<const TmaMaps *>(maps), so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k,
-                   iters, halo, tile, tiles_x, ntiles);
+        B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<false, TBOX_WIDE>), dim3(grid), dim3(NT),
+                   smem_tma_bytes(TBOX_WIDE), *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
+                   halo, tile, tiles_x, ntiles);
 }
 
 namespace {
@@ -434,11 +453,14 @@ cudaError_t tvl1_blocked_init() {
     if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
     e = cudaFuncSetAttribute(k_tvl1_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)SMEM_TMA_BYTES);
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, TBOX_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_tma_bytes(TBOX_WIDE));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)SMEM_TMA_BYTES);
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<false, TBOX_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_tma_bytes(TBOX_WIDE));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_tma_bytes(R));
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }
