@@ -26,6 +26,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# keep stdout to the one JSON line (some boxes export NCCL_DEBUG=VERSION, which prints to stdout)
+os.environ["NCCL_DEBUG"] = os.environ.get("B2F_NCCL_DEBUG", "WARN")
 
 H, W = 1080, 1920
 WORKLOADS = {
@@ -269,22 +271,36 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     "how": "separate profiled calls, CUDA events around every launch on the launching stream",
                     "all_classes_ms": {k: v["ms"] for k, v in st["classes"].items()}}
         alg.setProfiling(False)
-
-        # ---- e2e: host (pinned) buffers through b2f_calc_host, copies inside the timed region ----
-        nb = min(B, 16)
-        h_in = [torch.from_numpy(f).pin_memory() for f in frames_h[:nb + 1]]
-        h_out = torch.empty((nb, H, W, 2), dtype=torch.float32).pin_memory()
-        hp = [(h_in[i].numpy(), h_in[i + 1].numpy()) for i in range(nb)]
-        ho = [h_out[i].numpy() for i in range(nb)]
+        # DRAM traffic of the same kernel class from the committed ncu --set full capture (profiles/)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dom_name)
+            if tr:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_launch"] = tr["launch"]
+                roofline["traffic_algorithmic_bytes"] = tr["algorithmic_bytes_per_launch"]
+        except Exception:
+            pass
+    # ---- e2e: host (pinned) buffers through b2f_calc_host, copies inside the timed region; every rank
+    #      runs its own shard at the same time, the slowest rank sets the time ----
+    nb = min(B, 16)
+    h_in = [torch.from_numpy(f).pin_memory() for f in frames_h[:nb + 1]]
+    h_out = torch.empty((nb, H, W, 2), dtype=torch.float32).pin_memory()
+    hp = [(h_in[i].numpy(), h_in[i + 1].numpy()) for i in range(nb)]
+    ho = [h_out[i].numpy() for i in range(nb)]
+    batcher.run_host(hp, ho)
+    n_e2e = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
         batcher.run_host(hp, ho)
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
-            batcher.run_host(hp, ho)
-        dt = time.perf_counter() - t0
-        e2e = {"value": nb * n_e2e / dt, "unit": "1080p frame-pairs/s", "h2d_bytes_per_step": nb * 2 * H * W,
-               "d2h_bytes_per_step": nb * H * W * 8, "pairs_per_step": nb, "streams": args.streams,
-               "timing": "host wall clock around b2f_calc_host calls (each returns after its D2H completed)"}
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        e2e = {"value": world * nb * n_e2e / float(dt.item()), "unit": "1080p frame-pairs/s",
+               "h2d_bytes_per_step": world * nb * 2 * H * W, "d2h_bytes_per_step": world * nb * H * W * 8,
+               "pairs_per_step": world * nb, "streams": args.streams,
+               "timing": "host wall clock (max over ranks) around b2f_calc_host calls; each call returns after its D2H completed"}
         if not args.no_cpu:
             r = cpu_reference_run(args.workload, steps=3, warmup=1, budget_s=25.0)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
