@@ -372,11 +372,13 @@ __device__ __forceinline__ void farn_update_matrices_quad(const Stack5 &R0, cons
         float t00[4], t01[4], t10[4], t11[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float *p = base[e] + k * ps;
+            const float *p = base[e];
+            const float *p2 = p + pitch;
             t00[e] = __ldg(p);
             t01[e] = __ldg(p + 1);
-            t10[e] = __ldg(p + pitch);
-            t11[e] = __ldg(p + pitch + 1);
+            t10[e] = __ldg(p2);
+            t11[e] = __ldg(p2 + 1);
+            base[e] = p + ps;  // next plane
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) g[k][e] = a00[e] * t00[e] + a01[e] * t01[e] + a10[e] * t10[e] + a11[e] * t11[e];
@@ -543,15 +545,26 @@ __global__ void __launch_bounds__(256) k_farn_iter_fast(Stack5 Min, Stack5 Mout,
     for (int j = 0; j <= K; ++j) gk[j] = GAUSS ? g[j] : 1.f;
 
     // ---- vertical pass ----
+    const size_t plane_stride = (size_t)Min.h * Min.pitch;
     for (int task = tid; task < SW * 5 * 2; task += 256) {
         const int half = task / (SW * 5);
         const int rem = task - half * (SW * 5);
         const int pl = rem / SW, i = rem - pl * SW;
         const int xc = clampi(x0 + i - K, 0, cols - 1);
         const int yb = y0 + half * HALF - K;
+        const float *colp = Min.p + pl * plane_stride + xc;  // column base of this plane
         float v[WIN];
+        if (yb >= 0 && yb + WIN <= rows) {  // interior rows: walk the column with one pointer
+            const float *p = colp + (size_t)yb * Min.pitch;
 #pragma unroll
-        for (int q = 0; q < WIN; ++q) v[q] = __ldg(&Min.at(pl, clampi(yb + q, 0, rows - 1), xc));
+            for (int q = 0; q < WIN; ++q) {
+                v[q] = __ldg(p);
+                p += Min.pitch;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) v[q] = __ldg(colp + (size_t)clampi(yb + q, 0, rows - 1) * Min.pitch);
+        }
         float *dst = sm + ((size_t)pl * FT_H + half * HALF) * SW + i;
 #pragma unroll
         for (int o = 0; o < HALF; ++o) {
