@@ -263,6 +263,86 @@ __global__ void __launch_bounds__(256) k_brox_sor(BroxLevelPlanes P, Plane du_in
     dv_out.at(j, i) = dv;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused red-black SOR: `iters` full iterations (2*iters half sweeps) per launch on a 64x64 region held in
+// shared memory.  Each half sweep consumes one halo cell per side, so the centre (64 - 4*iters)^2 tile
+// is exact (bit-identical to `iters` pairs of k_brox_sor launches: a colour's update reads only the
+// other colour, so updating in place equals the reference's ping-pong).  A level that fits in one region
+// needs no halo at all and runs all solver iterations of an inner step in one launch.
+// ---------------------------------------------------------------------------------------------
+constexpr int SR = 64;           // region edge
+constexpr int S_THREADS = 512;
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+    k_brox_sor_fused_pp(BroxLevelPlanes P, Plane du_out, Plane dv_out, int h, int w, float omega, int iters, int halo,
+                        int tile) {
+    extern __shared__ float ssm[];
+    float *s_du = ssm, *s_dv = ssm + SR * SR, *s_u = ssm + 2 * SR * SR, *s_v = ssm + 3 * SR * SR;
+    float *s_sx = ssm + 4 * SR * SR, *s_sy = ssm + 5 * SR * SR, *s_iu = ssm + 6 * SR * SR, *s_iv = ssm + 7 * SR * SR;
+    float *s_nu = ssm + 8 * SR * SR, *s_nv = ssm + 9 * SR * SR, *s_nd = ssm + 10 * SR * SR;
+    const int tid = threadIdx.x;
+    const int gx0 = blockIdx.x * tile - halo, gy0 = blockIdx.y * tile - halo;
+
+    for (int idx = tid; idx < SR * SR; idx += S_THREADS) {
+        const int ry = idx >> 6, rx = idx & 63;
+        const int gy = gy0 + ry, gx = gx0 + rx;
+        const bool in = gx >= 0 && gy >= 0 && gx < w && gy < h;
+        s_du[idx] = in ? P.du.at(gy, gx) : 0.f;
+        s_dv[idx] = in ? P.dv.at(gy, gx) : 0.f;
+        s_u[idx] = in ? P.u.at(gy, gx) : 0.f;
+        s_v[idx] = in ? P.v.at(gy, gx) : 0.f;
+        s_sx[idx] = in ? P.sx.at(gy, gx) : 0.f;
+        s_sy[idx] = in ? P.sy.at(gy, gx) : 0.f;
+        s_iu[idx] = in ? P.inv_u.at(gy, gx) : 0.f;
+        s_iv[idx] = in ? P.inv_v.at(gy, gx) : 0.f;
+        s_nu[idx] = in ? P.num_u.at(gy, gx) : 0.f;
+        s_nv[idx] = in ? P.num_v.at(gy, gx) : 0.f;
+        s_nd[idx] = in ? P.num_dudv.at(gy, gx) : 0.f;
+    }
+    __syncthreads();
+
+    for (int sweep = 0; sweep < 2 * iters; ++sweep) {
+        const int colour = sweep & 1;  // sor_pass<0> first, then sor_pass<1> (NB:915-922)
+        for (int c = tid; c < SR * SR / 2; c += S_THREADS) {
+            const int ry = c >> 5;
+            const int rx = ((c & 31) << 1) + ((ry + gy0 + gx0 + colour) & 1);  // (gx + gy) % 2 == colour
+            const int gy = gy0 + ry, gx = gx0 + rx;
+            if (gx < 0 || gy < 0 || gx >= w || gy >= h) continue;
+            // region-edge cells read clamped region neighbours: their values are stale, but they lie in the halo
+            const int idx = ry * SR + rx;
+            const int il = (gx > 0 && rx > 0) ? idx - 1 : idx, ir = (gx < w - 1 && rx < SR - 1) ? idx + 1 : idx;
+            const int id = (gy > 0 && ry > 0) ? idx - SR : idx, iu = (gy < h - 1 && ry < SR - 1) ? idx + SR : idx;
+            const float s_left = s_sx[idx], s_down = s_sy[idx];
+            const float s_right = gx < w - 1 ? s_sx[ir] : 0.0f;
+            const float s_up = gy < h - 1 ? s_sy[iu] : 0.0f;
+            const float u = s_u[idx], v = s_v[idx];
+            float du = s_du[idx], dv = s_dv[idx];
+            const float ssum = s_left + s_right + s_up + s_down;
+            const float numerator_dudv = s_nd[idx];
+            const float numerator_u = (s_left * (s_u[il] + s_du[il]) + s_up * (s_u[iu] + s_du[iu]) +
+                                       s_right * (s_u[ir] + s_du[ir]) + s_down * (s_u[id] + s_du[id]) - u * ssum -
+                                       s_nu[idx] - numerator_dudv * dv);
+            du = (1.0f - omega) * du + omega * s_iu[idx] * numerator_u;
+            const float numerator_v = (s_left * (s_v[il] + s_dv[il]) + s_up * (s_v[iu] + s_dv[iu]) +
+                                       s_right * (s_v[ir] + s_dv[ir]) + s_down * (s_v[id] + s_dv[id]) - v * ssum -
+                                       s_nv[idx] - numerator_dudv * du);
+            dv = (1.0f - omega) * dv + omega * s_iv[idx] * numerator_v;
+            s_du[idx] = du;
+            s_dv[idx] = dv;
+        }
+        __syncthreads();
+    }
+
+    for (int idx = tid; idx < tile * tile; idx += S_THREADS) {
+        const int ty = idx / tile, tx = idx - ty * tile;
+        const int gy = gy0 + halo + ty, gx = gx0 + halo + tx;
+        if (gx < w && gy < h) {
+            du_out.at(gy, gx) = s_du[(halo + ty) * SR + halo + tx];
+            dv_out.at(gy, gx) = s_dv[(halo + ty) * SR + halo + tx];
+        }
+    }
+}
+
 // u += du ; v += dv  (NB:929-931), in place
 __global__ void __launch_bounds__(256) k_brox_add(Plane u, Plane v, Plane du, Plane dv, int h, int w) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,6 +493,7 @@ cudaError_t BroxEngine::ensure_workspace(int rows, int cols) {
 
 void BroxEngine::solve(Ctx &c) {
     const dim3 block(32, 8);
+    const size_t sor_smem = sizeof(float) * 11 * SR * SR;
     const float inv_sf = 1.0f / static_cast<float>(P.scale_factor);  // kernels get 1/xFactor (NS:2264,2270)
     const int nl = static_cast<int>(L_.levels.size());
     // restriction, level by level from the previous one
@@ -452,11 +533,39 @@ void BroxEngine::solve(Ctx &c) {
         for (int in = 0; in < P.inner_iterations; ++in) {
             B2F_LAUNCH(c, CLS_PREP, 104.0 * npx, k_brox_prepare, grid, block, 0, T, h, w, static_cast<float>(P.alpha),
                        static_cast<float>(P.gamma));
-            for (int s = 0; s < P.solver_iterations; ++s) {
-                const float omega = 1.99f;  // NB:914
-                B2F_LAUNCH(c, CLS_SOR, 26.0 * npx, k_brox_sor<0>, grid, block, 0, T, T.du, T.dv, dun, dvn, h, w, omega);
-                B2F_LAUNCH(c, CLS_SOR, 26.0 * npx, k_brox_sor<1>, grid, block, 0, T, dun, dvn, T.du, T.dv, h, w, omega);
-                c.stats->iterations_run++;
+            const float omega = 1.99f;  // NB:914
+            if (knobs.kernel_path != 1) {
+                // fused path: up to 5 full iterations per launch (all of them when the level fits one region).
+                // A CTA reads its halo from global memory that neighbouring CTAs overwrite with their centre
+                // tiles at the end, so launches ping-pong between (du, dv) and (dun, dvn).
+                int left = P.solver_iterations;
+                const bool single = w <= SR && h <= SR;  // whole level in one region: no halo, one launch
+                Plane cdu = T.du, cdv = T.dv, ndu = dun, ndv = dvn;
+                while (left > 0) {
+                    const int it = single ? left : (left < 5 ? left : 5);
+                    const int halo = single ? 0 : 2 * it;
+                    const int tile = single ? SR : SR - 2 * halo;
+                    const dim3 gs(single ? 1 : div_up(w, tile), single ? 1 : div_up(h, tile));
+                    BroxLevelPlanes Q = T;
+                    Q.du = cdu;
+                    Q.dv = cdv;
+                    B2F_LAUNCH(c, CLS_SOR, 52.0 * npx * it, k_brox_sor_fused_pp, gs, dim3(S_THREADS), sor_smem, Q, ndu, ndv,
+                               h, w, omega, it, halo, tile);
+                    Plane t1 = cdu; cdu = ndu; ndu = t1;
+                    Plane t2 = cdv; cdv = ndv; ndv = t2;
+                    left -= it;
+                    c.stats->iterations_run += it;
+                }
+                if (cdu.p != T.du.p) {  // odd number of launches: result sits in the spare pair -> swap roles
+                    Plane t1 = T.du; T.du = dun; dun = t1;
+                    Plane t2 = T.dv; T.dv = dvn; dvn = t2;
+                }
+            } else {
+                for (int s = 0; s < P.solver_iterations; ++s) {
+                    B2F_LAUNCH(c, CLS_SOR, 26.0 * npx, k_brox_sor<0>, grid, block, 0, T, T.du, T.dv, dun, dvn, h, w, omega);
+                    B2F_LAUNCH(c, CLS_SOR, 26.0 * npx, k_brox_sor<1>, grid, block, 0, T, dun, dvn, T.du, T.dv, h, w, omega);
+                    c.stats->iterations_run++;
+                }
             }
         }
         B2F_LAUNCH(c, CLS_PYR, 24.0 * npx, k_brox_add, grid, block, 0, T.u, T.v, T.du, T.dv, h, w);
@@ -487,6 +596,16 @@ int BroxEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
         return B2F_BAD_ARG;
     const int rows = I0->rows, cols = I0->cols;
     Ctx c = make_ctx(s);
+    {
+        static bool attr_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+            c.check(cudaFuncSetAttribute(k_brox_sor_fused_pp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(float) * 11 * SR * SR)));
+            attr_done[dev] = c.ok();
+        }
+    }
     c.check(ensure_workspace(rows, cols));
     if (!c.ok()) return finish(c, s);
     stats.levels = static_cast<int>(L_.levels.size());

@@ -40,6 +40,21 @@ def test_brox_matches_model(cuda_device, h, w, kind):
     assert alg.getDefaultName() == "DenseOpticalFlow.BroxOpticalFlow"
 
 
+def test_brox_fused_sor_bit_identical_to_half_sweep_kernels(cuda_device):
+    """kernel_path=1 runs one launch per red/black half sweep (the reference's shape); the default path
+    fuses up to 5 iterations per launch in shared memory.  Same arithmetic, same order -> same bits."""
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(150, 203, seed=7, kind="smooth", dtype="f32")
+    d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
+    outs = []
+    for path in (0, 1):
+        alg = ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, 3, 77, 7)
+        alg.setEngineOption("kernel_path", path)
+        outs.append(alg.calc(d0, d1).cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]), float(np.abs(outs[0] - outs[1]).max())
+
+
 def test_brox_reference_test_parameters_recover_motion(cuda_device):
     # the only parameter set the reference ever runs: create(0.197, 50, 0.8, 10, 77, 10) (test_optflow.cpp:75-76)
     I0, I1, gt = synth.make_pair(240, 320, seed=1, kind="const", dtype="f32")
