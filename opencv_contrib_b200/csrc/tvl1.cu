@@ -16,7 +16,6 @@
 #include "tvl1_blocked.cuh"
 
 #include <cmath>
-#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -39,60 +38,20 @@ struct Tvl1Planes {
 // as the reference's separate gradient pass, so I1x/I1y never touch HBM); taps use clamp
 // addressing exactly like the reference's point/clamp textures; I1w is not stored (dead).
 // ---------------------------------------------------------------------------------------------
-constexpr int WARP_TILE_W = 64, WARP_TILE_H = 32;  // shared I1 tile of the warp kernel
-
 __global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
                                                    Plane grad, Plane rho, int rows, int cols) {
-    __shared__ float tile[WARP_TILE_H * WARP_TILE_W];
-    __shared__ int red[4][8];
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const bool valid = x < cols && y < rows;
+    if (x >= cols || y >= rows) return;
 
-    float u1 = 0.f, u2 = 0.f;
-    if (valid) {
-        u1 = u1p.at(y, x);
-        u2 = u2p.at(y, x);
-    }
+    const float u1 = u1p.at(y, x);
+    const float u2 = u2p.at(y, x);
     const float wx = x + u1;
     const float wy = y + u2;
     const float fx = floorf(wx), fy = floorf(wy);
     // integer tap origin, kept in a range where int conversion is safe even for wild flows
     const int ix = static_cast<int>(fminf(fmaxf(fx, -8.f), cols + 8.f)) - 1;
     const int iy = static_cast<int>(fminf(fmaxf(fy, -8.f), rows + 8.f)) - 1;
-
-    // block-wide bounding box of the tap origins -> shared I1 tile when it is small and interior
-    int mnx = valid ? ix : INT_MAX, mxx = valid ? ix : INT_MIN, mny = valid ? iy : INT_MAX, mxy = valid ? iy : INT_MIN;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-    }
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    if ((tid & 31) == 0) {
-        red[0][tid >> 5] = mnx; red[1][tid >> 5] = mxx; red[2][tid >> 5] = mny; red[3][tid >> 5] = mxy;
-    }
-    __syncthreads();
-    mnx = red[0][0]; mxx = red[1][0]; mny = red[2][0]; mxy = red[3][0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) {
-        mnx = min(mnx, red[0][w]); mxx = max(mxx, red[1][w]); mny = min(mny, red[2][w]); mxy = max(mxy, red[3][w]);
-    }
-    const int bx0 = mnx - 1, by0 = mny - 1;              // window of a pixel: cols ix-1 .. ix+4
-    const int bw = mxx + 4 - bx0 + 1, bh = mxy + 4 - by0 + 1;
-    // interior only: clamped (border) taps need the per-tap path to reproduce the reference exactly
-    const bool use_tile = bw <= WARP_TILE_W && bh <= WARP_TILE_H && bx0 >= 0 && by0 >= 0 && bx0 + bw <= cols &&
-                          by0 + bh <= rows;
-    if (use_tile) {
-        for (int t = tid; t < bw * bh; t += 256) {
-            const int r = t / bw, c = t - r * bw;
-            tile[r * WARP_TILE_W + c] = __ldg(&I1.at(by0 + r, bx0 + c));
-        }
-    }
-    __syncthreads();
-    if (!valid) return;
 
     float kx[4], ky[4];
 #pragma unroll
@@ -103,29 +62,7 @@ __global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p
 
     float sum = 0.f, sumx = 0.f, sumy = 0.f, wsum = 0.f;
 
-    if (use_tile) {
-        // interior block: the 6x6 windows of all its pixels sit in the shared tile
-        const float *tb = tile + (iy - 1 - by0) * WARP_TILE_W + (ix - 1 - bx0);
-        float win[6][6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j)
-#pragma unroll
-            for (int i = 0; i < 6; ++i) win[j][i] = tb[j * WARP_TILE_W + i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float w = kx[i] * ky[j];
-                const float v = win[j + 1][i + 1];
-                const float gx = 0.5f * (win[j + 1][i + 2] - win[j + 1][i]);
-                const float gy = 0.5f * (win[j + 2][i + 1] - win[j][i + 1]);
-                sum = __fmaf_rn(w, v, sum);
-                sumx = __fmaf_rn(w, gx, sumx);
-                sumy = __fmaf_rn(w, gy, sumy);
-                wsum += w;
-            }
-        }
-    } else if (ix >= 1 && iy >= 1 && ix + 4 <= cols - 1 && iy + 4 <= rows - 1) {
+    if (ix >= 1 && iy >= 1 && ix + 4 <= cols - 1 && iy + 4 <= rows - 1) {
         // interior: 6x6 window, no clamping
         float win[6][6];
         const float *base = &I1.at(iy - 1, ix - 1);
@@ -512,40 +449,66 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
     const dim3 grid(div_up(cols, 32), div_up(rows, 8));
     const int nblocks = grid.x * grid.y;
 
-    const bool fixed_schedule = !(P.epsilon > 0.0);
-    const bool blocked_ok = fixed_schedule && !use_gamma && knobs.kernel_path != 1;
-
+    // The temporally blocked kernel needs gamma == 0; with epsilon > 0 it runs the stretches of iterations the
+    // reference's cadence does NOT sample (they can never end the loop), the sampled ones go through the
+    // unfused kernels with the deterministic error reduction.
+    const bool blocked_ok = !use_gamma && knobs.kernel_path != 1;
     Tvl1BlockedPlanes B;
     if (blocked_ok) blocked_planes(s, B);
     const bool use_tma = blocked_ok && tma_ok_ && knobs.kernel_path != 2;
     int cur = 0;  // which state set holds the current (u, p) in the blocked path
 
+    auto point_T_at = [&](int set) {  // unfused kernels work in place on the current state set
+        if (!blocked_ok) return;
+        T.u1 = B.s[set].u1; T.u2 = B.s[set].u2;
+        T.p11 = B.s[set].p11; T.p12 = B.s[set].p12; T.p21 = B.s[set].p21; T.p22 = B.s[set].p22;
+    };
+    auto run_blocked = [&](int count) {
+        int done = 0;
+        while (done < count) {
+            const int kk = tvl1_blocked_pick_k(knobs.fused_iters, count - done, rows, cols);
+            if (use_tma)
+                tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path != 3);
+            else
+                tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);
+            cur ^= 1;
+            done += kk;
+        }
+        c.stats->iterations_run += count;
+    };
+
     for (int w = 0; w < P.warps; ++w) {
-        const Plane wu1 = blocked_ok ? B.s[cur].u1 : T.u1;
-        const Plane wu2 = blocked_ok ? B.s[cur].u2 : T.u2;
-        B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, wu1, wu2, T.I1wx, T.I1wy,
+        point_T_at(cur);
+        B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy,
                    T.grad, T.rho_c, rows, cols);
 
-        if (blocked_ok) {
-            int done = 0;
-            while (done < P.iterations) {
-                const int kk = tvl1_blocked_pick_k(knobs.fused_iters, P.iterations - done, rows, cols);
-                if (use_tma)
-                    tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path != 3);
-                else
-                    tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);
-                cur ^= 1;
-                done += kk;
-            }
-            c.stats->iterations_run += P.iterations;
+        if (blocked_ok && !(P.epsilon > 0.0)) {  // fixed schedule
+            run_blocked(P.iterations);
             continue;
         }
 
         // reference cadence (tvl1flow.cpp:357-380)
         double error = std::numeric_limits<double>::max();
         double prevError = 0.0;
-        for (int n = 0; error > scaledEpsilon && n < P.iterations; ++n) {
+        int n = 0;
+        while (error > scaledEpsilon && n < P.iterations) {
             const bool calcError = (P.epsilon > 0) && (n & 1) && (prevError < scaledEpsilon);
+            if (!calcError && blocked_ok) {
+                // count the unsampled iterations ahead (each of them leaves error = DBL_MAX and
+                // prevError -= scaledEpsilon) and run them as one blocked stretch
+                int m = 0;
+                double pe = prevError;
+                while (n + m < P.iterations && !((P.epsilon > 0) && ((n + m) & 1) && (pe < scaledEpsilon))) {
+                    pe -= scaledEpsilon;
+                    ++m;
+                }
+                run_blocked(m);
+                prevError = pe;
+                error = std::numeric_limits<double>::max();
+                n += m;
+                continue;
+            }
+            point_T_at(cur);
             B2F_LAUNCH(c, CLS_ITER, 48.0 * npx, k_tvl1_estimate_u, grid, block, 0, T, rows, cols, k,
                        calcError ? 1 : 0, L_.partials);
             if (calcError) {
@@ -563,6 +526,7 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
             }
             B2F_LAUNCH(c, CLS_ITER, 40.0 * npx, k_tvl1_estimate_dual, grid, block, 0, T, rows, cols, k);
             c.stats->iterations_run++;
+            ++n;
         }
     }
 
