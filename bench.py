@@ -194,6 +194,49 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+def side_measurements(workload: str, pairs, flow_views, dev):
+    """Secondary single-stream numbers for the other BASELINE configs (not the headline `value`):
+    device-resident, CUDA events, after the main timed region."""
+    import torch
+    import opencv_contrib_b200 as ocb
+    out = {}
+
+    def time_alg(alg, a, b, f, n):
+        for _ in range(2):
+            alg.calc(a, b, f)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            alg.calc(a, b, f)
+        e1.record()
+        torch.cuda.synchronize()
+        return 1000.0 * n / e0.elapsed_time(e1)
+
+    a, b = pairs[0]
+    f = flow_views[0]
+    try:
+        if workload != "farneback":
+            out["farneback_1080p_default_pairs_per_s_1stream"] = time_alg(ocb.FarnebackOpticalFlow_create(), a, b, f, 10)
+        if workload != "tvl1":
+            out["tvl1_1080p_5x10x30_eps0_pairs_per_s_1stream"] = time_alg(
+                ocb.OpticalFlowDual_TVL1_create(nscales=5, warps=10, epsilon=0.0, iterations=30), a, b, f, 5)
+        # the reference's create() defaults (5 warps, <= 300 iterations, epsilon 0.01: data-dependent early exit)
+        alg = ocb.OpticalFlowDual_TVL1_create()
+        out["tvl1_1080p_reference_defaults_eps0.01_pairs_per_s_1stream"] = time_alg(alg, a, b, f, 5)
+        out["tvl1_1080p_reference_defaults_iterations_run"] = alg.getStats()["iterations_run"]
+        # BASELINE configs[3]: Brox 1280x720, the reference's only parameter set (10, 77, 10)
+        bx = (a[:720, :1280].float() / 255.0).contiguous()
+        by = (b[:720, :1280].float() / 255.0).contiguous()
+        bf = torch.empty((720, 1280, 2), dtype=torch.float32, device=dev)
+        out["brox_720p_10_77_10_pairs_per_s_1stream"] = time_alg(
+            ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, 10, 77, 10), bx, by, bf, 3)
+        out["denselk_1080p_default_pairs_per_s_1stream"] = time_alg(ocb.DensePyrLKOpticalFlow_create(), a, b, f, 3)
+    except Exception as e:  # side numbers must never break the headline line
+        out["error"] = repr(e)
+    return out
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args, rank: int, local_rank: int, world: int):
     import numpy as np
@@ -249,6 +292,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     roofline = None
     e2e = None
     cpu = None
+    extras = None
     if rank == 0:
         alg = make_alg(args.workload)
         alg.calc(*pairs[0], flow_views[0])
@@ -304,6 +348,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if not args.no_cpu:
             r = cpu_reference_run(args.workload, steps=3, warmup=1, budget_s=25.0)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        extras = side_measurements(args.workload, pairs, flow_views, dev) if not args.no_extras else None
 
     if rank == 0:
         line = {
@@ -317,6 +362,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "l2": "inputs per step (%.0f MB u8) exceed the 126 MB L2; engine working set ~0.3 GB/pair" % (
                            B * 2 * H * W / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -333,6 +379,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=32, help="frame pairs per step per GPU")
     ap.add_argument("--streams", type=int, default=4, help="engine instances / CUDA streams per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary single-stream measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
