@@ -205,6 +205,89 @@ B2F_API const char *b2f_kernel_class_name(const b2f_handle *h, int cls);
  * bypassed) so per-class device time can be read back with b2f_get_stats. */
 B2F_API int b2f_set_profiling(b2f_handle *h, int on);
 
+
+/* =============================================================================================
+ * Adjacent components: what sits directly either side of calc().
+ * ============================================================================================= */
+
+/* ---- planar output: same contract as b2f_calc but the flow is written as two 32FC1 planes.
+ *      The reference's consumers call calc() and then cuda::split (superres/src/optical_flow.cpp:
+ *      557-574, 816-835); this skips the merge + split round trip.  With the algorithm's
+ *      use-initial-flow option the planes are read first. ---- */
+B2F_API int b2f_calc_uv(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_image *u, b2f_image *v,
+                        void *cuda_stream);
+
+/* ---- cv::cuda::interpolateFrames (cudalegacy.hpp:229, src/interpolate_frames.cpp:54-111,
+ *      src/cuda/NPP_staging.cu:1648-1790 nppiStInterpolateFrames, :1838-1905 forward splat).
+ *   frame0, frame1, fu, fv, bu, bv : device 32FC1 images of one size AND one step (the reference
+ *            asserts equal steps, interpolate_frames.cpp:82).
+ *   pos    : time position in [0,1].
+ *   new_frame : device 32FC1 output, same size/step.
+ *   buf    : device 32FC1 scratch of 6*rows x cols, same step, laid out like the reference's
+ *            (coverage0, coverage1, fwdU, fwdV, bwdU, bwdV); zeroed by the call.
+ *   flags  : B2F_INTERP_REFERENCE reproduces the reference bit-for-bit in formula, including its
+ *            three defects (the 4th splat lands in bwdU a second time so bwdV stays 0,
+ *            NPP_staging.cu:1779-1787; both samples of the "visible in both" branch read frame0,
+ *            :1666; the coverage clear indexes by width not stride, :1985-1996);
+ *            B2F_INTERP_CORRECTED fixes the three.  Float atomics: the sum order is not fixed,
+ *            results agree to rounding (as in the reference). ---- */
+enum { B2F_INTERP_REFERENCE = 0, B2F_INTERP_CORRECTED = 1 };
+B2F_API int b2f_interpolate_frames(const b2f_image *frame0, const b2f_image *frame1, const b2f_image *fu,
+                                   const b2f_image *fv, const b2f_image *bu, const b2f_image *bv, float pos,
+                                   b2f_image *new_frame, b2f_image *buf, int flags, void *cuda_stream);
+
+/* ---- video front end: consecutive frames of one stream -> flow(k-1 -> k).
+ *      Each pushed HOST frame is uploaded once (the previous frame stays resident), the solve for
+ *      pair k overlaps the upload of frame k+1 and the download of flow k-1 (three streams, events,
+ *      no host synchronisation inside push), and with `warm_start` the previous pair's flow seeds
+ *      the next solve (tvl1flow.cpp:203-207,249-256 useInitialFlow; farneback.cpp:179-188,398-404
+ *      OPTFLOW_USE_INITIAL_FLOW; the temporal chaining the reference's test does by hand,
+ *      test_optflow.cpp:328-334).  `depth` = pairs in flight (ring of host-visible results). ---- */
+typedef struct b2f_video b2f_video;
+B2F_API int b2f_video_create(b2f_handle *h, int rows, int cols, int type, int depth, int warm_start,
+                             b2f_video **out);
+/* Enqueue frame k (host pointer, `step` bytes per row; pinned memory makes the copy asynchronous).
+ * For k >= 1 a solve for pair (k-1, k) is enqueued and *pair_index receives k-1; for k = 0 it
+ * receives -1.  Blocks only when `depth` pairs are already in flight. */
+B2F_API int b2f_video_push(b2f_video *v, const void *host_frame, size_t step, int64_t *pair_index);
+/* Wait for pair `pair_index` and copy its 32FC2 flow to host memory (`step` bytes per row).
+ * Pairs must be fetched before they fall `depth` behind the newest push. */
+B2F_API int b2f_video_fetch(b2f_video *v, int64_t pair_index, void *host_flow, size_t step);
+B2F_API void b2f_video_destroy(b2f_video *v);
+
+/* ---- Middlebury .flo files and the reference's error measures (host side).
+ *      Format: float tag 202021.25 ("PIEH"), int32 width, int32 height, then rows of interleaved
+ *      (u, v) float32 (optflow/test/test_tvl1optflow.cpp:49-108,
+ *      optflow/samples/optical_flow_evaluation.cpp:23-71). ---- */
+B2F_API int b2f_flo_read_size(const char *path, int *rows, int *cols);
+B2F_API int b2f_flo_read(const char *path, float *flow, size_t step, int rows, int cols);
+B2F_API int b2f_flo_write(const char *path, const float *flow, size_t step, int rows, int cols);
+
+enum { B2F_ERR_ENDPOINT = 0, B2F_ERR_ANGULAR_REFERENCE = 1, B2F_ERR_ANGULAR = 2 };
+/* Per-pixel error map between two HOST 32FC2 fields (NaN where either flow is invalid: NaN or
+ * |component| >= 1e9, optical_flow_evaluation.cpp:23-26).  B2F_ERR_ANGULAR_REFERENCE keeps the
+ * sample's operator precedence, acos(u1.u2 / |u1| * |u2|) (:67); B2F_ERR_ANGULAR is the intended
+ * acos(u1.u2 / (|u1| |u2|)). */
+B2F_API int b2f_flow_error_map(const float *flow1, size_t step1, const float *flow2, size_t step2, int rows,
+                               int cols, int measure, float *err, size_t err_step);
+typedef struct b2f_error_stats {
+    double mean, stddev;   /* meanStdDev over the mask (:126-130)                          */
+    double r[5];           /* fraction with error > {0.5, 1, 2, 5, 10} (:74-93,133-139)    */
+    double a[3];           /* error value at the {0.5, 0.75, 0.95} quantiles from a        */
+                           /* 1024-bin histogram over [0, max] (:94-105,141-163)           */
+    double max;
+    int64_t count;         /* masked pixels                                                */
+} b2f_error_stats;
+/* mask: optional HOST 8-bit mask (non-zero = use), NULL = all pixels.  NaN errors compare false
+ * in the R statistics and are skipped by mean/std/histogram, as OpenCV's primitives do. */
+B2F_API int b2f_flow_error_stats(const float *err, size_t err_step, const unsigned char *mask, size_t mask_step,
+                                 int rows, int cols, b2f_error_stats *out);
+/* The reference's regression criterion (test_tvl1optflow.cpp:114-142): among gold pixels that are
+ * valid, the fraction whose squared endpoint error is <= threshold^2; a test passes when it is
+ * >= expected accuracy (0.95 at threshold 0.1). */
+B2F_API int b2f_flow_accuracy(const float *gold, size_t gold_step, const float *flow, size_t flow_step, int rows,
+                              int cols, double threshold, double *fraction);
+
 #ifdef __cplusplus
 }
 #endif

@@ -238,5 +238,21 @@ public:
 
 #undef B2F_ACCESSOR
 
+/** cv::cuda::interpolateFrames (cudalegacy.hpp:229, src/interpolate_frames.cpp:54-111): same argument order;
+ *  newFrame and buf are (re)allocated like the reference does (:64-67).  `corrected` = false keeps the
+ *  reference's behaviour including its defects (see b200flow.h). */
+inline void interpolateFrames(const GpuMat &frame0, const GpuMat &frame1, const GpuMat &fu, const GpuMat &fv,
+                              const GpuMat &bu, const GpuMat &bv, float pos, GpuMat &newFrame, GpuMat &buf,
+                              Stream &stream = Stream::Null(), bool corrected = false) {
+    newFrame.create(frame0.rows, frame0.cols, frame0.type());
+    buf.create(6 * frame0.rows, frame0.cols, frame0.type());
+    auto img = [](const GpuMat &m) { return b2f_image{m.data, m.step, m.rows, m.cols, m.type()}; };
+    b2f_image f0 = img(frame0), f1 = img(frame1), iu = img(fu), iv = img(fv), ju = img(bu), jv = img(bv);
+    b2f_image out = img(newFrame), scratch = img(buf);
+    const int st = b2f_interpolate_frames(&f0, &f1, &iu, &iv, &ju, &jv, pos, &out, &scratch,
+                                          corrected ? B2F_INTERP_CORRECTED : B2F_INTERP_REFERENCE, detail::raw(stream));
+    if (st != B2F_OK) detail::fail(st, "interpolateFrames");
+}
+
 }  // namespace cuda
 }  // namespace b200flow

@@ -7,6 +7,9 @@ Only what the hot path needs lives here:
   cudaoptflow.py   Python mirror of the reference's generated bindings
                    (cv2.cuda.OpticalFlowDual_TVL1_create(...).calc(I0, I1, flow, stream))
   batch.py         batched frame-pair front end, one process per GPU (torch.distributed / NCCL)
+  video.py         consecutive-frame front end (one upload per frame, warm start, 3-stream pipeline)
+  frames.py        interpolateFrames, the consumer right after the solvers
+  flowio.py        Middlebury .flo files + the reference's error statistics
 """
 from .cudaoptflow import (  # noqa: F401
     DenseOpticalFlow,
@@ -22,3 +25,6 @@ from .cudaoptflow import (  # noqa: F401
     OPTFLOW_FARNEBACK_GAUSSIAN,
 )
 from ._lib import B2FError  # noqa: F401
+from .frames import interpolateFrames  # noqa: F401
+from .video import VideoFlow  # noqa: F401
+from . import flowio  # noqa: F401

@@ -57,8 +57,15 @@ class b2f_stats(C.Structure):
                 ("levels", C.c_int), ("iterations_run", C.c_int)]
 
 
+class b2f_error_stats(C.Structure):
+    _fields_ = [("mean", C.c_double), ("stddev", C.c_double), ("r", C.c_double * 5), ("a", C.c_double * 3),
+                ("max", C.c_double), ("count", C.c_int64)]
+
+
 # every symbol include/b200flow.h declares: (name, restype, argtypes)
 _H = C.c_void_p
+_IMG = C.POINTER(b2f_image)
+_F = C.POINTER(C.c_float)
 SYMBOLS = [
     ("b2f_tvl1_default_params", None, [C.POINTER(b2f_tvl1_params)]),
     ("b2f_farneback_default_params", None, [C.POINTER(b2f_farneback_params)]),
@@ -82,6 +89,23 @@ SYMBOLS = [
     ("b2f_reset_stats", C.c_int, [_H]),
     ("b2f_kernel_class_name", C.c_char_p, [_H, C.c_int]),
     ("b2f_set_profiling", C.c_int, [_H, C.c_int]),
+    # adjacent components
+    ("b2f_calc_uv", C.c_int, [_H, _IMG, _IMG, _IMG, _IMG, C.c_void_p]),
+    ("b2f_interpolate_frames", C.c_int, [_IMG, _IMG, _IMG, _IMG, _IMG, _IMG, C.c_float, _IMG, _IMG, C.c_int,
+                                         C.c_void_p]),
+    ("b2f_video_create", C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
+    ("b2f_video_push", C.c_int, [_H, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]),
+    ("b2f_video_fetch", C.c_int, [_H, C.c_int64, C.c_void_p, C.c_size_t]),
+    ("b2f_video_destroy", None, [_H]),
+    ("b2f_flo_read_size", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("b2f_flo_read", C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
+    ("b2f_flo_write", C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
+    ("b2f_flow_error_map", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_size_t]),
+    ("b2f_flow_error_stats", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                       C.POINTER(b2f_error_stats)]),
+    ("b2f_flow_accuracy", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_double,
+                                    C.POINTER(C.c_double)]),
 ]
 
 # b2f_param_id values (include/b200flow.h)

@@ -586,7 +586,7 @@ int BroxEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
     // preconditions: brox.cpp:134-135 (CV_32FC1, equal size/type), NB:606-617
     if (I0->type != B2F_32FC1 || I1->type != B2F_32FC1) return B2F_UNSUPPORTED_TYPE;
     if (I0->rows != I1->rows || I0->cols != I1->cols) return B2F_SIZE_MISMATCH;
-    if (flow->type != B2F_32FC2) return B2F_UNSUPPORTED_TYPE;
+    if (!flow_type_ok(flow)) return B2F_UNSUPPORTED_TYPE;
     if (flow->rows != I0->rows || flow->cols != I0->cols) return B2F_SIZE_MISMATCH;
     if (!(P.alpha > 0.0) || P.gamma < 0.0 || P.inner_iterations <= 0 || P.outer_iterations <= 0 ||
         P.solver_iterations <= 0)
@@ -613,7 +613,7 @@ int BroxEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
 
     const ImageView v0{I0->data, I0->step, rows, cols, I0->type};
     const ImageView v1{I1->data, I1->step, rows, cols, I1->type};
-    const ImageView vf{flow->data, flow->step, rows, cols, B2F_32FC2};
+    const ImageView vf = flow_view(flow, rows, cols);
     convert_pair(c, CLS_PYR, v0, v1, L_.levels[0].I0, L_.levels[0].I1, 1.0f);  // NB:714-718 copy into aligned planes
 
     const bool want_graph = knobs.use_graph && !profiling && s != nullptr;

@@ -35,6 +35,8 @@ struct ImageView {
     void *data;
     size_t step;  // bytes
     int rows, cols, type;
+    void *data2 = nullptr;  // planar flow output (b2f_calc_uv): data = u plane, data2 = v plane
+    size_t step2 = 0;
 };
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -115,6 +117,18 @@ struct b2f_handle {
     b2f::Arena arena;
     std::vector<b2f::Ctx::Timed> timed;
     std::vector<cudaEvent_t> event_pool;
+    // planar flow output requested by b2f_calc_uv for the duration of one calc()
+    void *planar_v = nullptr;
+    size_t planar_v_step = 0;
+    bool flow_type_ok(const b2f_image *flow) const {
+        return planar_v ? flow->type == B2F_32FC1 : flow->type == B2F_32FC2;
+    }
+    b2f::ImageView flow_view(const b2f_image *flow, int rows, int cols) const {
+        b2f::ImageView v{flow->data, flow->step, rows, cols, planar_v ? B2F_32FC1 : B2F_32FC2};
+        v.data2 = planar_v;
+        v.step2 = planar_v_step;
+        return v;
+    }
     // staging for b2f_calc_host
     void *host_stage = nullptr;
     size_t host_stage_bytes = 0;

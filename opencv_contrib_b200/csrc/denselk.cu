@@ -191,7 +191,7 @@ int DenseLKEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flo
     // preconditions, pyrlk.cpp:240-243
     if (I0->type != B2F_8UC1 || I1->type != B2F_8UC1) return B2F_UNSUPPORTED_TYPE;
     if (I0->rows != I1->rows || I0->cols != I1->cols) return B2F_SIZE_MISMATCH;
-    if (flow->type != B2F_32FC2) return B2F_UNSUPPORTED_TYPE;
+    if (!flow_type_ok(flow)) return B2F_UNSUPPORTED_TYPE;
     if (flow->rows != I0->rows || flow->cols != I0->cols) return B2F_SIZE_MISMATCH;
     if (P.max_level < 0 || !(P.win_width > 2 && P.win_height > 2) || P.iters < 0) return B2F_BAD_ARG;
     if (I0->step < (size_t)I0->cols || I1->step < (size_t)I1->cols || flow->step < (size_t)flow->cols * 8) return B2F_BAD_ARG;
@@ -215,7 +215,7 @@ int DenseLKEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flo
 
     const ImageView v0{I0->data, I0->step, rows, cols, I0->type};
     const ImageView v1{I1->data, I1->step, rows, cols, I1->type};
-    const ImageView vf{flow->data, flow->step, rows, cols, B2F_32FC2};
+    const ImageView vf = flow_view(flow, rows, cols);
     convert_pair(c, CLS_PYR, v0, v1, L_.levels[0].I, L_.levels[0].J, 1.0f);  // convertTo(CV_32F), pyrlk.cpp:252-253
     for (int l = 1; l <= P.max_level; ++l) {
         const LLevel &a = L_.levels[l - 1], &b = L_.levels[l];

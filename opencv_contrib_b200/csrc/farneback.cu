@@ -803,7 +803,7 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
     if (!(I0->type == B2F_8UC1 || I0->type == B2F_32FC1)) return B2F_UNSUPPORTED_TYPE;
     if (I0->type != I1->type) return B2F_UNSUPPORTED_TYPE;
     if (I0->rows != I1->rows || I0->cols != I1->cols) return B2F_SIZE_MISMATCH;
-    if (flow->type != B2F_32FC2) return B2F_UNSUPPORTED_TYPE;
+    if (!flow_type_ok(flow)) return B2F_UNSUPPORTED_TYPE;
     if (flow->rows != I0->rows || flow->cols != I0->cols) return B2F_SIZE_MISMATCH;
     if (!(P.poly_n == 5 || P.poly_n == 7)) return B2F_BAD_ARG;
     if (P.fast_pyramids && !(std::abs(P.pyr_scale - 0.5) < 1e-6)) return B2F_BAD_ARG;
@@ -836,7 +836,7 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
 
     const ImageView v0{I0->data, I0->step, rows, cols, I0->type};
     const ImageView v1{I1->data, I1->step, rows, cols, I1->type};
-    const ImageView vf{flow->data, flow->step, rows, cols, B2F_32FC2};
+    const ImageView vf = flow_view(flow, rows, cols);
     const dim3 block(32, 8);
 
     convert_pair(c, CLS_IMG, v0, v1, L.frames[0], L.frames[1], 1.0f);  // convertTo(CV_32F), farneback.cpp:342-345

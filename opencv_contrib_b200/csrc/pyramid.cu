@@ -174,6 +174,15 @@ void resize_linear_one(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, 
 }
 
 void merge_flow(Ctx &c, int cls, Plane u, Plane v, const ImageView &flow) {
+    if (flow.data2) {  // planar output: two pitched device-to-device copies
+        if (!c.ok()) return;
+        const size_t w = sizeof(float) * (size_t)flow.cols;
+        c.check(cudaMemcpy2DAsync(flow.data, flow.step, u.p, sizeof(float) * (size_t)u.pitch, w, flow.rows,
+                                  cudaMemcpyDeviceToDevice, c.stream));
+        c.check(cudaMemcpy2DAsync(flow.data2, flow.step2, v.p, sizeof(float) * (size_t)v.pitch, w, flow.rows,
+                                  cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
     const dim3 block(32, 8);
     const dim3 grid = grid2d(flow.cols, flow.rows, 1);
     B2F_LAUNCH(c, cls, 16.0 * flow.rows * flow.cols, k_merge, grid, block, 0, u, v, static_cast<float *>(flow.data),
@@ -181,6 +190,15 @@ void merge_flow(Ctx &c, int cls, Plane u, Plane v, const ImageView &flow) {
 }
 
 void split_flow(Ctx &c, int cls, const ImageView &flow, Plane u, Plane v) {
+    if (flow.data2) {
+        if (!c.ok()) return;
+        const size_t w = sizeof(float) * (size_t)flow.cols;
+        c.check(cudaMemcpy2DAsync(u.p, sizeof(float) * (size_t)u.pitch, flow.data, flow.step, w, flow.rows,
+                                  cudaMemcpyDeviceToDevice, c.stream));
+        c.check(cudaMemcpy2DAsync(v.p, sizeof(float) * (size_t)v.pitch, flow.data2, flow.step2, w, flow.rows,
+                                  cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
     const dim3 block(32, 8);
     const dim3 grid = grid2d(flow.cols, flow.rows, 1);
     B2F_LAUNCH(c, cls, 16.0 * flow.rows * flow.cols, k_split, grid, block, 0, static_cast<const float *>(flow.data),

@@ -168,6 +168,23 @@ int b2f_calc(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_image 
     return h->calc(I0, I1, flow, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int b2f_calc_uv(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_image *u, b2f_image *v,
+                void *cuda_stream) {
+    if (!h || !v) return B2F_BAD_ARG;
+    int st = check_images(I0, I1, u);
+    if (st != B2F_OK) return st;
+    if (!v->data) return B2F_BAD_ARG;
+    if (u->type != B2F_32FC1 || v->type != B2F_32FC1) return B2F_UNSUPPORTED_TYPE;
+    if (v->rows != u->rows || v->cols != u->cols) return B2F_SIZE_MISMATCH;
+    h->stats.calls++;
+    h->planar_v = v->data;
+    h->planar_v_step = v->step;
+    st = h->calc(I0, I1, u, static_cast<cudaStream_t>(cuda_stream));
+    h->planar_v = nullptr;
+    h->planar_v_step = 0;
+    return st;
+}
+
 static size_t elem_size(int type) {
     switch (type) {
         case B2F_8UC1: return 1;

@@ -569,7 +569,7 @@ int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
     if (!(I0->type == B2F_8UC1 || I0->type == B2F_32FC1)) return B2F_UNSUPPORTED_TYPE;
     if (I0->type != I1->type) return B2F_UNSUPPORTED_TYPE;
     if (I0->rows != I1->rows || I0->cols != I1->cols) return B2F_SIZE_MISMATCH;
-    if (flow->type != B2F_32FC2) return B2F_UNSUPPORTED_TYPE;
+    if (!flow_type_ok(flow)) return B2F_UNSUPPORTED_TYPE;
     if (flow->rows != I0->rows || flow->cols != I0->cols) return B2F_SIZE_MISMATCH;
     if (P.nscales <= 0) return B2F_BAD_ARG;
     if (P.warps < 0 || P.iterations < 0) return B2F_BAD_ARG;
@@ -588,7 +588,7 @@ int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
 
     const ImageView v0{I0->data, I0->step, rows, cols, I0->type};
     const ImageView v1{I1->data, I1->step, rows, cols, I1->type};
-    const ImageView vf{flow->data, flow->step, rows, cols, B2F_32FC2};
+    const ImageView vf = flow_view(flow, rows, cols);
 
     // convertTo(CV_32F, 8U ? 1 : 255), tvl1flow.cpp:200-201
     convert_pair(c, CLS_PYR, v0, v1, L_.levels[0].I0, L_.levels[0].I1, I0->type == B2F_8UC1 ? 1.0f : 255.0f);

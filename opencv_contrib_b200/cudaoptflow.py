@@ -98,6 +98,24 @@ class DenseOpticalFlow:
             raise B2FError(st, self._lib.b2f_last_cuda_error(self._h))
         return flow
 
+    def calcUV(self, I0, I1, u=None, v=None, stream=None):
+        """Planar variant: calc + cuda::split in one call (b2f_calc_uv; the reference's consumers split
+        the CV_32FC2 result themselves, superres/src/optical_flow.cpp:557-574).  Returns (u, v)."""
+        torch = _torch()
+        if u is None:
+            u = torch.empty((I0.shape[0], I0.shape[1]), dtype=torch.float32, device=I0.device)
+        if v is None:
+            v = torch.empty_like(u)
+        i0, i1 = _image_from_tensor(I0), _image_from_tensor(I1)
+        iu, iv = _image_from_tensor(u), _image_from_tensor(v)
+        if stream is None:
+            stream = torch.cuda.current_stream(I0.device)
+        sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        st = self._lib.b2f_calc_uv(self._h, C.byref(i0), C.byref(i1), C.byref(iu), C.byref(iv), C.c_void_p(sptr))
+        if st != 0:
+            raise B2FError(st, self._lib.b2f_last_cuda_error(self._h))
+        return u, v
+
     def calc_host(self, I0: np.ndarray, I1: np.ndarray, flow: np.ndarray | None = None, stream=None):
         """Host-buffer variant (upload + calc + download inside the call; b2f_calc_host)."""
         if flow is None:

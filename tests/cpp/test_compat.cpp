@@ -64,6 +64,41 @@ int main(int argc, char **argv) {
     FILE *f = fopen(argv[6], "wb");
     fwrite(out.data(), 4, out.size(), f);
     fclose(f);
+    if (argc >= 8) {
+        // the consumer right after calc (cudalegacy interpolateFrames): forward flow as computed, backward flow
+        // approximated by its negation, frames as CV_32FC1 in [0, 1]; the Python side repeats the same call
+        std::vector<float> f0((size_t)rows * cols), f1(f0.size()), pu(f0.size()), pv(f0.size()), nu(f0.size()), nv(f0.size());
+        for (size_t i = 0; i < f0.size(); ++i) {
+            f0[i] = h0[i] / 255.f;
+            f1[i] = h1[i] / 255.f;
+            pu[i] = out[2 * i];
+            pv[i] = out[2 * i + 1];
+            nu[i] = -pu[i];
+            nv[i] = -pv[i];
+        }
+        cvcuda::GpuMat g0(rows, cols, 5 /*CV_32FC1*/), g1(rows, cols, 5), gu(rows, cols, 5), gv(rows, cols, 5),
+            hu(rows, cols, 5), hv(rows, cols, 5), mid, buf;
+        const size_t hs = (size_t)cols * 4;
+        g0.upload(f0.data(), hs, stream);
+        g1.upload(f1.data(), hs, stream);
+        gu.upload(pu.data(), hs, stream);
+        gv.upload(pv.data(), hs, stream);
+        hu.upload(nu.data(), hs, stream);
+        hv.upload(nv.data(), hs, stream);
+        try {
+            cvcuda::interpolateFrames(g0, g1, gu, gv, hu, hv, 0.5f, mid, buf, stream);
+        } catch (const std::exception &e) {
+            fprintf(stderr, "exception: %s\n", e.what());
+            return 6;
+        }
+        if (buf.rows != 6 * rows || mid.rows != rows || mid.type() != 5) return 7;
+        std::vector<float> m((size_t)rows * cols);
+        mid.download(m.data(), hs, stream);
+        stream.waitForCompletion();
+        FILE *g = fopen(argv[7], "wb");
+        fwrite(m.data(), 4, m.size(), g);
+        fclose(g);
+    }
     printf("ok %d %d type=%d step=%zu\n", flow.rows, flow.cols, flow.type(), flow.step);
     return 0;
 }
