@@ -232,6 +232,35 @@ def side_measurements(workload: str, pairs, flow_views, dev):
         out["brox_720p_10_77_10_pairs_per_s_1stream"] = time_alg(
             ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, 10, 77, 10), bx, by, bf, 3)
         out["denselk_1080p_default_pairs_per_s_1stream"] = time_alg(ocb.DensePyrLKOpticalFlow_create(), a, b, f, 3)
+        # video front end (one upload per frame, 3-stream pipeline): host frames in, host flows out
+        import time
+        import numpy as np
+        hf = [x.cpu().numpy() for (x, _) in pairs[:9]]
+        for name, make in (("tvl1_5x10x30_eps0", lambda: ocb.OpticalFlowDual_TVL1_create(nscales=5, warps=10, epsilon=0.0,
+                                                                                       iterations=30)),
+                           ("farneback_default", lambda: ocb.FarnebackOpticalFlow_create())):
+            vf = ocb.VideoFlow(make(), H, W, dtype=np.uint8, depth=3)
+            seq = [hf[i % len(hf)] for i in range(25)]
+            for _ in vf.run(seq[:4], copy=False):
+                pass
+            t0 = time.perf_counter()
+            n = sum(1 for _ in vf.run(seq, copy=False))
+            out["video_%s_1080p_pairs_per_s_host_to_host" % name] = n / (time.perf_counter() - t0)
+            vf.close()
+        # interpolateFrames, the consumer right after calc (cudalegacy), 1080p
+        u, v = (torch.randn((H, W), device=dev) * 3 for _ in range(2))
+        f0, f1 = a.float() / 255.0, b.float() / 255.0
+        mid, buf = torch.empty_like(f0), torch.empty((6 * H, W), device=dev)
+        for _ in range(2):
+            ocb.interpolateFrames(f0, f1, u, v, -u, -v, 0.5, mid, buf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            ocb.interpolateFrames(f0, f1, u, v, -u, -v, 0.5, mid, buf)
+        e1.record()
+        torch.cuda.synchronize()
+        out["interpolate_frames_1080p_frames_per_s"] = 20000.0 / e0.elapsed_time(e1)
     except Exception as e:  # side numbers must never break the headline line
         out["error"] = repr(e)
     return out

@@ -253,6 +253,9 @@ B2F_API int b2f_video_push(b2f_video *v, const void *host_frame, size_t step, in
 /* Wait for pair `pair_index` and copy its 32FC2 flow to host memory (`step` bytes per row).
  * Pairs must be fetched before they fall `depth` behind the newest push. */
 B2F_API int b2f_video_fetch(b2f_video *v, int64_t pair_index, void *host_flow, size_t step);
+/* Zero-copy variant: waits for the pair and returns a pointer into the front end's pinned result ring
+ * (rows of `*step` bytes).  The memory stays valid until `depth` further pairs have been pushed. */
+B2F_API int b2f_video_fetch_view(b2f_video *v, int64_t pair_index, const float **host_flow, size_t *step);
 B2F_API void b2f_video_destroy(b2f_video *v);
 
 /* ---- Middlebury .flo files and the reference's error measures (host side).
@@ -278,8 +281,9 @@ typedef struct b2f_error_stats {
     double max;
     int64_t count;         /* masked pixels                                                */
 } b2f_error_stats;
-/* mask: optional HOST 8-bit mask (non-zero = use), NULL = all pixels.  NaN errors compare false
- * in the R statistics and are skipped by mean/std/histogram, as OpenCV's primitives do. */
+/* mask: optional HOST 8-bit mask (non-zero = use), NULL = all pixels.  A NaN error propagates through
+ * mean/stddev as it does through cv::meanStdDev, compares false in the R statistics and lands in no
+ * histogram bin. */
 B2F_API int b2f_flow_error_stats(const float *err, size_t err_step, const unsigned char *mask, size_t mask_step,
                                  int rows, int cols, b2f_error_stats *out);
 /* The reference's regression criterion (test_tvl1optflow.cpp:114-142): among gold pixels that are

@@ -96,6 +96,7 @@ SYMBOLS = [
     ("b2f_video_create", C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
     ("b2f_video_push", C.c_int, [_H, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]),
     ("b2f_video_fetch", C.c_int, [_H, C.c_int64, C.c_void_p, C.c_size_t]),
+    ("b2f_video_fetch_view", C.c_int, [_H, C.c_int64, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t)]),
     ("b2f_video_destroy", None, [_H]),
     ("b2f_flo_read_size", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("b2f_flo_read", C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),

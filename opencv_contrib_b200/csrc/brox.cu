@@ -160,62 +160,109 @@ struct BroxLevelPlanes {
     Plane I0, I1, Ix, Ixx, Ix0, Iy, Iyy, Iy0, Ixy;
     Plane u, v, du, dv;
     Plane sx, sy, inv_u, inv_v, num_dudv, num_u, num_v;
+    // warped image terms, constant over the inner iterations of a level (they depend on (u, v) only)
+    Plane wIz, wIx, wIxz, wIxy, wIxx, wIy, wIyz, wIyy;
 };
 
-// diffusivity between (i,j) and (i-1,j)  (NB:188-204)
-__device__ __forceinline__ float brox_sx(const Plane &u, const Plane &v, const Plane &du, const Plane &dv, int h, int w,
-                                         int j, int i) {
-    auto L = [&](const Plane &P, int y, int x) { return __ldg(&P.at(mirror_load(y, h), mirror_load(x, w))); };
-    const float u_x = L(u, j, i) + L(du, j, i) - L(u, j, i - 1) - L(du, j, i - 1);
-    const float v_x = L(v, j, i) + L(dv, j, i) - L(v, j, i - 1) - L(dv, j, i - 1);
-    const float u_y = 0.25f * (L(u, j + 1, i) + L(du, j + 1, i) + L(u, j + 1, i - 1) + L(du, j + 1, i - 1) -
-                               L(u, j - 1, i) - L(du, j - 1, i) - L(u, j - 1, i - 1) - L(du, j - 1, i - 1));
-    const float v_y = 0.25f * (L(v, j + 1, i) + L(dv, j + 1, i) + L(v, j + 1, i - 1) + L(dv, j + 1, i - 1) -
-                               L(v, j - 1, i) - L(dv, j - 1, i) - L(v, j - 1, i - 1) - L(dv, j - 1, i - 1));
+// Shared-memory tile of (u, du, v, dv) with a 1-cell halo, mirror-addressed like load_array_element (NB:238-319).
+constexpr int PB_X = 32, PB_Y = 8;
+constexpr int PT_W = PB_X + 2, PT_H = PB_Y + 2;
+struct PrepTile {
+    float u[PT_H][PT_W], du[PT_H][PT_W], v[PT_H][PT_W], dv[PT_H][PT_W];
+};
+// diffusivity between (i,j) and (i-1,j)  (NB:188-204); (ty, tx) = tile coordinates of (j, i)
+__device__ __forceinline__ float brox_sx(const PrepTile &T, int ty, int tx) {
+    const float u_x = T.u[ty][tx] + T.du[ty][tx] - T.u[ty][tx - 1] - T.du[ty][tx - 1];
+    const float v_x = T.v[ty][tx] + T.dv[ty][tx] - T.v[ty][tx - 1] - T.dv[ty][tx - 1];
+    const float u_y = 0.25f * (T.u[ty + 1][tx] + T.du[ty + 1][tx] + T.u[ty + 1][tx - 1] + T.du[ty + 1][tx - 1] -
+                               T.u[ty - 1][tx] - T.du[ty - 1][tx] - T.u[ty - 1][tx - 1] - T.du[ty - 1][tx - 1]);
+    const float v_y = 0.25f * (T.v[ty + 1][tx] + T.dv[ty + 1][tx] + T.v[ty + 1][tx - 1] + T.dv[ty + 1][tx - 1] -
+                               T.v[ty - 1][tx] - T.dv[ty - 1][tx] - T.v[ty - 1][tx - 1] - T.dv[ty - 1][tx - 1]);
     return 0.5f / sqrtf(u_x * u_x + v_x * v_x + u_y * u_y + v_y * v_y + EPS2);
 }
 // diffusivity between (i,j) and (i,j-1)  (NB:216-227)
-__device__ __forceinline__ float brox_sy(const Plane &u, const Plane &v, const Plane &du, const Plane &dv, int h, int w,
-                                         int j, int i) {
-    auto L = [&](const Plane &P, int y, int x) { return __ldg(&P.at(mirror_load(y, h), mirror_load(x, w))); };
-    const float u_y = L(u, j, i) + L(du, j, i) - L(u, j - 1, i) - L(du, j - 1, i);
-    const float v_y = L(v, j, i) + L(dv, j, i) - L(v, j - 1, i) - L(dv, j - 1, i);
-    const float u_x = 0.25f * (L(u, j, i + 1) + L(u, j - 1, i + 1) + L(du, j, i + 1) + L(du, j - 1, i + 1) -
-                               L(u, j, i - 1) - L(u, j - 1, i - 1) - L(du, j, i - 1) - L(du, j - 1, i - 1));
-    const float v_x = 0.25f * (L(v, j, i + 1) + L(v, j - 1, i + 1) + L(dv, j, i + 1) + L(dv, j - 1, i + 1) -
-                               L(v, j, i - 1) - L(v, j - 1, i - 1) - L(dv, j, i - 1) - L(dv, j - 1, i - 1));
+__device__ __forceinline__ float brox_sy(const PrepTile &T, int ty, int tx) {
+    const float u_y = T.u[ty][tx] + T.du[ty][tx] - T.u[ty - 1][tx] - T.du[ty - 1][tx];
+    const float v_y = T.v[ty][tx] + T.dv[ty][tx] - T.v[ty - 1][tx] - T.dv[ty - 1][tx];
+    const float u_x = 0.25f * (T.u[ty][tx + 1] + T.u[ty - 1][tx + 1] + T.du[ty][tx + 1] + T.du[ty - 1][tx + 1] -
+                               T.u[ty][tx - 1] - T.u[ty - 1][tx - 1] - T.du[ty][tx - 1] - T.du[ty - 1][tx - 1]);
+    const float v_x = 0.25f * (T.v[ty][tx + 1] + T.v[ty - 1][tx + 1] + T.dv[ty][tx + 1] + T.dv[ty - 1][tx + 1] -
+                               T.v[ty][tx - 1] - T.v[ty - 1][tx - 1] - T.dv[ty][tx - 1] - T.dv[ty - 1][tx - 1]);
     return 0.5f / sqrtf(u_x * u_x + v_x * v_x + u_y * u_y + v_y * v_y + EPS2);
 }
 
-__global__ void __launch_bounds__(256) k_brox_prepare(BroxLevelPlanes P, int h, int w, float alpha, float gamma) {
+// The texture fetches of prepare_sor_stage_1 (NB:352-383): I1 and its derivatives sampled at the warped
+// position ((x + u) / w, (y + v) / h), I0 and its derivatives at the pixel centre.  (u, v) do not change
+// during the inner iterations of a level -- only (du, dv) do -- so the reference's 9 bilinear fetches per
+// pixel per inner iteration are evaluated once per level here and re-read as 8 coalesced planes.
+__global__ void __launch_bounds__(256) k_brox_warp_terms(BroxLevelPlanes P, int h, int w) {
     const int ig = blockIdx.x * blockDim.x + threadIdx.x;
     const int jg = blockIdx.y * blockDim.y + threadIdx.y;
     if (ig >= w || jg >= h) return;
     float x = (float)ig + 0.5f, y = (float)jg + 0.5f;
     const float uu = P.u.at(jg, ig), vv = P.v.at(jg, ig);
-    const float du = P.du.at(jg, ig), dv = P.dv.at(jg, ig);
     const float wx = (x + uu) / (float)w, wy = (y + vv) / (float)h;
     x /= (float)w;
     y /= (float)h;
-    const float Iz = tex_bilinear(P.I1, h, w, wx, wy) - tex_bilinear(P.I0, h, w, x, y);
     const float Ix = tex_bilinear(P.Ix, h, w, wx, wy);
-    const float Ixz = Ix - tex_bilinear(P.Ix0, h, w, x, y);
-    const float Ixy = tex_bilinear(P.Ixy, h, w, wx, wy);
-    const float Ixx = tex_bilinear(P.Ixx, h, w, wx, wy);
     const float Iy = tex_bilinear(P.Iy, h, w, wx, wy);
-    const float Iyz = Iy - tex_bilinear(P.Iy0, h, w, x, y);
-    const float Iyy = tex_bilinear(P.Iyy, h, w, wx, wy);
+    P.wIz.at(jg, ig) = tex_bilinear(P.I1, h, w, wx, wy) - tex_bilinear(P.I0, h, w, x, y);
+    P.wIx.at(jg, ig) = Ix;
+    P.wIxz.at(jg, ig) = Ix - tex_bilinear(P.Ix0, h, w, x, y);
+    P.wIxy.at(jg, ig) = tex_bilinear(P.Ixy, h, w, wx, wy);
+    P.wIxx.at(jg, ig) = tex_bilinear(P.Ixx, h, w, wx, wy);
+    P.wIy.at(jg, ig) = Iy;
+    P.wIyz.at(jg, ig) = Iy - tex_bilinear(P.Iy0, h, w, x, y);
+    P.wIyy.at(jg, ig) = tex_bilinear(P.Iyy, h, w, wx, wy);
+}
+
+// prepare_sor_stage_1 + stage_2 fused (NB:340-473).  The smoothness diffusivities are computed once per cell
+// edge from a shared tile (each is needed by the two cells it separates) instead of four 24-load evaluations
+// per pixel; the data term samples the warped image and its derivatives in software.
+__global__ void __launch_bounds__(PB_X *PB_Y) k_brox_prepare(BroxLevelPlanes P, int h, int w, float alpha, float gamma) {
+    __shared__ PrepTile T;
+    __shared__ float s_sx[PB_Y][PB_X + 1];   // sx at tile columns 0..32
+    __shared__ float s_sy[PB_Y + 1][PB_X];   // sy at tile rows 0..8
+    const int tid = threadIdx.y * PB_X + threadIdx.x;
+    const int gx0 = blockIdx.x * PB_X, gy0 = blockIdx.y * PB_Y;
+    for (int t = tid; t < PT_W * PT_H; t += PB_X * PB_Y) {
+        const int ry = t / PT_W, rx = t - ry * PT_W;
+        const int y = mirror_load(gy0 - 1 + ry, h), x = mirror_load(gx0 - 1 + rx, w);
+        T.u[ry][rx] = P.u.at(y, x);
+        T.du[ry][rx] = P.du.at(y, x);
+        T.v[ry][rx] = P.v.at(y, x);
+        T.dv[ry][rx] = P.dv.at(y, x);
+    }
+    __syncthreads();
+    constexpr int N_SX = PB_Y * (PB_X + 1), N_SY = (PB_Y + 1) * PB_X;
+    for (int t = tid; t < N_SX + N_SY; t += PB_X * PB_Y) {
+        if (t < N_SX) {
+            const int ry = t / (PB_X + 1), rx = t - ry * (PB_X + 1);
+            const int gy = gy0 + ry, gx = gx0 + rx;
+            // sx = 0 at i = 0 (NB:396) and beyond the image (stage 2 treats it as zero, NB:440-452)
+            s_sx[ry][rx] = (gx == 0 || gx >= w || gy >= h) ? 0.f : brox_sx(T, ry + 1, rx + 1);
+        } else {
+            const int q = t - N_SX;
+            const int ry = q / PB_X, rx = q - ry * PB_X;
+            const int gy = gy0 + ry, gx = gx0 + rx;
+            s_sy[ry][rx] = (gy == 0 || gy >= h || gx >= w) ? 0.f : brox_sy(T, ry + 1, rx + 1);
+        }
+    }
+    __syncthreads();
+
+    const int ig = gx0 + threadIdx.x, jg = gy0 + threadIdx.y;
+    if (ig >= w || jg >= h) return;
+    const float du = T.du[threadIdx.y + 1][threadIdx.x + 1], dv = T.dv[threadIdx.y + 1][threadIdx.x + 1];
+    const float Iz = P.wIz.at(jg, ig), Ix = P.wIx.at(jg, ig), Ixz = P.wIxz.at(jg, ig), Ixy = P.wIxy.at(jg, ig);
+    const float Ixx = P.wIxx.at(jg, ig), Iy = P.wIy.at(jg, ig), Iyz = P.wIyz.at(jg, ig), Iyy = P.wIyy.at(jg, ig);
     const float q0 = Iz + Ix * du + Iy * dv;
     const float q1 = Ixz + Ixx * du + Ixy * dv;
     const float q2 = Iyz + Ixy * du + Iyy * dv;
     float data_term = 0.5f * rsqrtf(q0 * q0 + gamma * (q1 * q1 + q2 * q2) + EPS2);
     data_term /= alpha;
 
-    // smoothness diffusivities of this pixel and of its right / upper neighbours (stage 2 needs them)
-    const float sx = ig == 0 ? 0.f : brox_sx(P.u, P.v, P.du, P.dv, h, w, jg, ig);
-    const float sy = jg == 0 ? 0.f : brox_sy(P.u, P.v, P.du, P.dv, h, w, jg, ig);
-    const float sxr = ig + 1 < w ? brox_sx(P.u, P.v, P.du, P.dv, h, w, jg, ig + 1) : 0.f;
-    const float syu = jg + 1 < h ? brox_sy(P.u, P.v, P.du, P.dv, h, w, jg + 1, ig) : 0.f;
+    const float sx = s_sx[threadIdx.y][threadIdx.x], sxr = s_sx[threadIdx.y][threadIdx.x + 1];
+    const float sy = s_sy[threadIdx.y][threadIdx.x], syu = s_sy[threadIdx.y + 1][threadIdx.x];
 
     P.num_dudv.at(jg, ig) = data_term * (Ix * Iy + gamma * Ixy * (Ixx + Iyy));
     P.num_u.at(jg, ig) = data_term * (Ix * Iz + gamma * (Ixx * Ixz + Ixy * Iyz));
@@ -227,6 +274,42 @@ __global__ void __launch_bounds__(256) k_brox_prepare(BroxLevelPlanes P, int h, 
     const float dsum = sx + sxr + sy + syu;
     P.inv_u.at(jg, ig) = 1.0f / (den_u + dsum);
     P.inv_v.at(jg, ig) = 1.0f / (den_v + dsum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One SOR cell update (NB:501-547) with every rounding made explicit, shared by the three solver kernels
+// so that they agree bit for bit.  U* / V* are the neighbours' (u + du) / (v + dv); usum = u * ssum and
+// w_u = omega * inv_denom_u are per-cell constants of an inner step (the products the reference's
+// left-to-right expression forms first), so the register-resident kernel can hoist them.
+// ---------------------------------------------------------------------------------------------
+struct SorConst {
+    float s_l, s_r, s_u, s_d;   // diffusivities towards the four neighbours (0 beyond the image)
+    float usum, vsum;           // u * (s_l + s_r + s_u + s_d), v * (...)
+    float num_u, num_v, num_dudv;
+    float w_u, w_v;             // omega * inv_denom
+};
+__device__ __forceinline__ float brox_ssum(float s_l, float s_r, float s_u, float s_d) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(s_l, s_r), s_u), s_d);
+}
+__device__ __forceinline__ void brox_sor_cell(const SorConst &c, float Ul, float Uu, float Ur, float Ud, float Vl,
+                                              float Vu, float Vr, float Vd, float one_minus_omega, float &du,
+                                              float &dv) {
+    float t = __fmul_rn(c.s_l, Ul);
+    t = __fmaf_rn(c.s_u, Uu, t);
+    t = __fmaf_rn(c.s_r, Ur, t);
+    t = __fmaf_rn(c.s_d, Ud, t);
+    t = __fsub_rn(t, c.usum);
+    t = __fsub_rn(t, c.num_u);
+    t = __fmaf_rn(-c.num_dudv, dv, t);
+    du = __fmaf_rn(c.w_u, t, __fmul_rn(one_minus_omega, du));
+    t = __fmul_rn(c.s_l, Vl);
+    t = __fmaf_rn(c.s_u, Vu, t);
+    t = __fmaf_rn(c.s_r, Vr, t);
+    t = __fmaf_rn(c.s_d, Vd, t);
+    t = __fsub_rn(t, c.vsum);
+    t = __fsub_rn(t, c.num_v);
+    t = __fmaf_rn(-c.num_dudv, du, t);  // uses the NEW du (NB:538-545)
+    dv = __fmaf_rn(c.w_v, t, __fmul_rn(one_minus_omega, dv));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,22 +325,23 @@ __global__ void __launch_bounds__(256) k_brox_sor(BroxLevelPlanes P, Plane du_in
     if (((i + j) & 1) == IS_BLACK) {
         const int ir = i < w - 1 ? i + 1 : i, il = i > 0 ? i - 1 : i;
         const int ju = j < h - 1 ? j + 1 : j, jd = j > 0 ? j - 1 : j;
-        const float s_left = P.sx.at(j, i), s_down = P.sy.at(j, i);
-        const float s_right = i < w - 1 ? P.sx.at(j, ir) : 0.0f;
-        const float s_up = j < h - 1 ? P.sy.at(ju, i) : 0.0f;
-        const float u = P.u.at(j, i), v = P.v.at(j, i);
-        const float ssum = s_left + s_right + s_up + s_down;
-        const float numerator_dudv = P.num_dudv.at(j, i);
-        const float numerator_u =
-            (s_left * (P.u.at(j, il) + du_in.at(j, il)) + s_up * (P.u.at(ju, i) + du_in.at(ju, i)) +
-             s_right * (P.u.at(j, ir) + du_in.at(j, ir)) + s_down * (P.u.at(jd, i) + du_in.at(jd, i)) - u * ssum -
-             P.num_u.at(j, i) - numerator_dudv * dv);
-        du = (1.0f - omega) * du + omega * P.inv_u.at(j, i) * numerator_u;
-        const float numerator_v =
-            (s_left * (P.v.at(j, il) + dv_in.at(j, il)) + s_up * (P.v.at(ju, i) + dv_in.at(ju, i)) +
-             s_right * (P.v.at(j, ir) + dv_in.at(j, ir)) + s_down * (P.v.at(jd, i) + dv_in.at(jd, i)) - v * ssum -
-             P.num_v.at(j, i) - numerator_dudv * du);
-        dv = (1.0f - omega) * dv + omega * P.inv_v.at(j, i) * numerator_v;
+        SorConst c;
+        c.s_l = P.sx.at(j, i);
+        c.s_d = P.sy.at(j, i);
+        c.s_r = i < w - 1 ? P.sx.at(j, ir) : 0.0f;
+        c.s_u = j < h - 1 ? P.sy.at(ju, i) : 0.0f;
+        const float ssum = brox_ssum(c.s_l, c.s_r, c.s_u, c.s_d);
+        c.usum = __fmul_rn(P.u.at(j, i), ssum);
+        c.vsum = __fmul_rn(P.v.at(j, i), ssum);
+        c.num_u = P.num_u.at(j, i);
+        c.num_v = P.num_v.at(j, i);
+        c.num_dudv = P.num_dudv.at(j, i);
+        c.w_u = __fmul_rn(omega, P.inv_u.at(j, i));
+        c.w_v = __fmul_rn(omega, P.inv_v.at(j, i));
+        auto U = [&](int y, int x) { return __fadd_rn(P.u.at(y, x), du_in.at(y, x)); };
+        auto V = [&](int y, int x) { return __fadd_rn(P.v.at(y, x), dv_in.at(y, x)); };
+        brox_sor_cell(c, U(j, il), U(ju, i), U(j, ir), U(jd, i), V(j, il), V(ju, i), V(j, ir), V(jd, i), 1.0f - omega, du,
+                      dv);
     }
     du_out.at(j, i) = du;
     dv_out.at(j, i) = dv;
@@ -312,21 +396,23 @@ __global__ void __launch_bounds__(S_THREADS, 1)
             const int idx = ry * SR + rx;
             const int il = (gx > 0 && rx > 0) ? idx - 1 : idx, ir = (gx < w - 1 && rx < SR - 1) ? idx + 1 : idx;
             const int id = (gy > 0 && ry > 0) ? idx - SR : idx, iu = (gy < h - 1 && ry < SR - 1) ? idx + SR : idx;
-            const float s_left = s_sx[idx], s_down = s_sy[idx];
-            const float s_right = gx < w - 1 ? s_sx[ir] : 0.0f;
-            const float s_up = gy < h - 1 ? s_sy[iu] : 0.0f;
-            const float u = s_u[idx], v = s_v[idx];
+            SorConst cc;
+            cc.s_l = s_sx[idx];
+            cc.s_d = s_sy[idx];
+            cc.s_r = gx < w - 1 ? s_sx[ir] : 0.0f;
+            cc.s_u = gy < h - 1 ? s_sy[iu] : 0.0f;
+            const float ssum = brox_ssum(cc.s_l, cc.s_r, cc.s_u, cc.s_d);
+            cc.usum = __fmul_rn(s_u[idx], ssum);
+            cc.vsum = __fmul_rn(s_v[idx], ssum);
+            cc.num_u = s_nu[idx];
+            cc.num_v = s_nv[idx];
+            cc.num_dudv = s_nd[idx];
+            cc.w_u = __fmul_rn(omega, s_iu[idx]);
+            cc.w_v = __fmul_rn(omega, s_iv[idx]);
             float du = s_du[idx], dv = s_dv[idx];
-            const float ssum = s_left + s_right + s_up + s_down;
-            const float numerator_dudv = s_nd[idx];
-            const float numerator_u = (s_left * (s_u[il] + s_du[il]) + s_up * (s_u[iu] + s_du[iu]) +
-                                       s_right * (s_u[ir] + s_du[ir]) + s_down * (s_u[id] + s_du[id]) - u * ssum -
-                                       s_nu[idx] - numerator_dudv * dv);
-            du = (1.0f - omega) * du + omega * s_iu[idx] * numerator_u;
-            const float numerator_v = (s_left * (s_v[il] + s_dv[il]) + s_up * (s_v[iu] + s_dv[iu]) +
-                                       s_right * (s_v[ir] + s_dv[ir]) + s_down * (s_v[id] + s_dv[id]) - v * ssum -
-                                       s_nv[idx] - numerator_dudv * du);
-            dv = (1.0f - omega) * dv + omega * s_iv[idx] * numerator_v;
+            auto U = [&](int q) { return __fadd_rn(s_u[q], s_du[q]); };
+            auto V = [&](int q) { return __fadd_rn(s_v[q], s_dv[q]); };
+            brox_sor_cell(cc, U(il), U(iu), U(ir), U(id), V(il), V(iu), V(ir), V(id), 1.0f - omega, du, dv);
             s_du[idx] = du;
             s_dv[idx] = dv;
         }
@@ -339,6 +425,189 @@ __global__ void __launch_bounds__(S_THREADS, 1)
         if (gx < w && gy < h) {
             du_out.at(gy, gx) = s_du[(halo + ty) * SR + halo + tx];
             dv_out.at(gy, gx) = s_dv[(halo + ty) * SR + halo + tx];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident fused SOR (default path).  Same region / halo scheme as k_brox_sor_fused_pp, but a
+// thread owns a 2-column x 4-row patch of the 64x64 region and keeps its eight cells' (du, dv, u + du,
+// v + dv) and hoisted constants in registers; the rest of the per-cell constants sit in shared memory in
+// a colour-major layout that every warp reads conflict-free with 128-bit loads.  Horizontal neighbours
+// come from the own patch or one warp shuffle, vertical neighbours from the own patch except across the
+// 4-row boundary, where the two boundary rows are exchanged through shared memory (one barrier per half
+// sweep).  Shared-memory traffic per cell update drops from 31 two-way-conflicting word loads to two
+// conflict-free 128-bit loads.  Bit-identical to the other two solver kernels (brox_sor_cell).
+// ---------------------------------------------------------------------------------------------
+struct SorRegs {
+    float du, dv, U, V, u, v, usum, vsum, w_v;
+};
+
+template <int CP0>
+__device__ __forceinline__ void brox_half_sweep(SorRegs (&c)[4][2], const float4 *__restrict__ sS,
+                                                const float4 *__restrict__ sN, float *__restrict__ xU,
+                                                float *__restrict__ xV, int lane, int ry0, int rx0, int gx0, int gy0,
+                                                int w, int h, float one_minus_omega) {
+    // neighbours across the 4-row boundary (the other colour: written in the previous half sweep)
+    const int cpT = CP0, cpB = CP0 ^ 1;  // active column in patch rows 0 and 3
+    const int below = (ry0 > 0 ? ry0 - 1 : ry0) * SR + rx0 + cpT;
+    const int above = (ry0 + 4 < SR ? ry0 + 4 : ry0 + 3) * SR + rx0 + cpB;
+    const float Ud0 = xU[below], Vd0 = xV[below];
+    const float Uu3 = xU[above], Vu3 = xV[above];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int cp = (CP0 ^ r) & 1;  // compile-time after unrolling
+        const int gy = gy0 + ry0 + r, gx = gx0 + rx0 + cp;
+        // horizontal neighbours: the other column of the own patch, or the adjacent lane's
+        const float Uo = c[r][cp ^ 1].U, Vo = c[r][cp ^ 1].V;
+        float Ux, Vx;  // value from the neighbouring lane
+        if (cp == 0) {
+            Ux = __shfl_up_sync(0xffffffffu, Uo, 1);
+            Vx = __shfl_up_sync(0xffffffffu, Vo, 1);
+        } else {
+            Ux = __shfl_down_sync(0xffffffffu, Uo, 1);
+            Vx = __shfl_down_sync(0xffffffffu, Vo, 1);
+        }
+        SorRegs &me = c[r][cp];
+        const bool active = gx >= 0 && gy >= 0 && gx < w && gy < h;
+        float Ul, Ur, Vl, Vr;
+        if (cp == 0) {
+            const bool edge = lane == 0 || gx <= 0;
+            Ul = edge ? me.U : Ux;
+            Vl = edge ? me.V : Vx;
+            const bool redge = gx >= w - 1;
+            Ur = redge ? me.U : Uo;
+            Vr = redge ? me.V : Vo;
+        } else {
+            const bool edge = gx <= 0;
+            Ul = edge ? me.U : Uo;
+            Vl = edge ? me.V : Vo;
+            const bool redge = lane == 31 || gx >= w - 1;
+            Ur = redge ? me.U : Ux;
+            Vr = redge ? me.V : Vx;
+        }
+        float Ud, Vd, Uu, Vu;
+        if (r == 0) {
+            Ud = Ud0;
+            Vd = Vd0;
+        } else {
+            Ud = c[r > 0 ? r - 1 : 0][cp].U;
+            Vd = c[r > 0 ? r - 1 : 0][cp].V;
+        }
+        if (r == 3) {
+            Uu = Uu3;
+            Vu = Vu3;
+        } else {
+            Uu = c[r < 3 ? r + 1 : 3][cp].U;
+            Vu = c[r < 3 ? r + 1 : 3][cp].V;
+        }
+        if (gy <= 0 || (r == 0 && ry0 == 0)) {
+            Ud = me.U;
+            Vd = me.V;
+        }
+        if (gy >= h - 1 || (r == 3 && ry0 + 4 == SR)) {
+            Uu = me.U;
+            Vu = me.V;
+        }
+        const int slot = ((ry0 + r) * 2 + cp) * 32 + lane;
+        const float4 S = sS[slot], N = sN[slot];
+        SorConst k;
+        k.s_l = S.x; k.s_r = S.y; k.s_u = S.z; k.s_d = S.w;
+        k.num_u = N.x; k.num_v = N.y; k.num_dudv = N.z; k.w_u = N.w;
+        k.usum = me.usum; k.vsum = me.vsum; k.w_v = me.w_v;
+        float du = me.du, dv = me.dv;
+        brox_sor_cell(k, Ul, Uu, Ur, Ud, Vl, Vu, Vr, Vd, one_minus_omega, du, dv);
+        if (active) {
+            me.du = du;
+            me.dv = dv;
+            me.U = __fadd_rn(me.u, du);
+            me.V = __fadd_rn(me.v, dv);
+        }
+    }
+    // publish the updated boundary cells for the neighbouring warps' next half sweep
+    xU[ry0 * SR + rx0 + cpT] = c[0][cpT].U;
+    xV[ry0 * SR + rx0 + cpT] = c[0][cpT].V;
+    xU[(ry0 + 3) * SR + rx0 + cpB] = c[3][cpB].U;
+    xV[(ry0 + 3) * SR + rx0 + cpB] = c[3][cpB].V;
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+    k_brox_sor_reg(BroxLevelPlanes P, Plane du_out, Plane dv_out, int h, int w, float omega, int iters, int halo,
+                   int tile) {
+    extern __shared__ float4 sor4[];
+    float4 *sS = sor4;                 // [row][colour-parity][k] : s_l, s_r, s_u, s_d
+    float4 *sN = sor4 + SR * SR;       // same layout            : num_u, num_v, num_dudv, omega * inv_u
+    float *xU = reinterpret_cast<float *>(sor4 + 2 * SR * SR);  // boundary-row exchange, [row][col]
+    float *xV = xU + SR * SR;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rx0 = 2 * lane, ry0 = 4 * warp;
+    const int gx0 = blockIdx.x * tile - halo, gy0 = blockIdx.y * tile - halo;  // both even
+
+    SorRegs c[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int gy = gy0 + ry0 + r, gx = gx0 + rx0 + q;
+            const bool in = gx >= 0 && gy >= 0 && gx < w && gy < h;
+            SorRegs &m = c[r][q];
+            float4 S = make_float4(0.f, 0.f, 0.f, 0.f), N = make_float4(0.f, 0.f, 0.f, 0.f);
+            m.du = m.dv = m.u = m.v = m.usum = m.vsum = m.w_v = 0.f;
+            if (in) {
+                m.du = P.du.at(gy, gx);
+                m.dv = P.dv.at(gy, gx);
+                m.u = P.u.at(gy, gx);
+                m.v = P.v.at(gy, gx);
+                S.x = P.sx.at(gy, gx);
+                S.w = P.sy.at(gy, gx);
+                S.y = gx < w - 1 ? P.sx.at(gy, gx + 1) : 0.0f;
+                S.z = gy < h - 1 ? P.sy.at(gy + 1, gx) : 0.0f;
+                const float ssum = brox_ssum(S.x, S.y, S.z, S.w);
+                m.usum = __fmul_rn(m.u, ssum);
+                m.vsum = __fmul_rn(m.v, ssum);
+                N.x = P.num_u.at(gy, gx);
+                N.y = P.num_v.at(gy, gx);
+                N.z = P.num_dudv.at(gy, gx);
+                N.w = __fmul_rn(omega, P.inv_u.at(gy, gx));
+                m.w_v = __fmul_rn(omega, P.inv_v.at(gy, gx));
+            }
+            m.U = __fadd_rn(m.u, m.du);
+            m.V = __fadd_rn(m.v, m.dv);
+            const int slot = ((ry0 + r) * 2 + q) * 32 + lane;
+            sS[slot] = S;
+            sN[slot] = N;
+            if (r == 0 || r == 3) {
+                xU[(ry0 + r) * SR + rx0 + q] = m.U;
+                xV[(ry0 + r) * SR + rx0 + q] = m.V;
+            }
+        }
+    }
+    __syncthreads();
+
+    const float omo = 1.0f - omega;
+    // colour 0 first (sor_pass<0>, NB:915-922): cells with (gx + gy) even; gx0 is even, so in patch row 0 the
+    // active column is (colour ^ gy0 ^ ry0) & 1 = (colour ^ gy0) & 1 -- uniform over the CTA
+    const int par = gy0 & 1;
+    for (int sweep = 0; sweep < 2 * iters; ++sweep) {
+        if (((sweep ^ par) & 1) == 0)
+            brox_half_sweep<0>(c, sS, sN, xU, xV, lane, ry0, rx0, gx0, gy0, w, h, omo);
+        else
+            brox_half_sweep<1>(c, sS, sN, xU, xV, lane, ry0, rx0, gx0, gy0, w, h, omo);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ry = ry0 + r, gy = gy0 + ry;
+        if (ry < halo || ry >= halo + tile || gy >= h) continue;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int rx = rx0 + q, gx = gx0 + rx;
+            if (rx < halo || rx >= halo + tile || gx >= w) continue;
+            du_out.at(gy, gx) = c[r][q].du;
+            dv_out.at(gy, gx) = c[r][q].dv;
         }
     }
 }
@@ -417,16 +686,16 @@ private:
         int rows = 0, cols = 0;
         b2f_brox_params P{};
         std::vector<BLevel> levels;
-        float *shared[20] = {};
+        float *shared[32] = {};
     };
     Layout L_;
     enum { S_IX = 0, S_IXX, S_IX0, S_IY, S_IYY, S_IY0, S_IXY, S_U, S_V, S_UN, S_VN, S_DU, S_DV, S_DUN, S_DVN, S_SX, S_SY,
-           S_INVU, S_INVV, S_NDUDV, S_COUNT };
+           S_INVU, S_INVV, S_NDUDV, S_WIZ, S_WIX, S_WIXZ, S_WIXY, S_WIXX, S_WIY, S_WIYZ, S_WIYY, S_COUNT };
     float *extra_[2] = {};  // num_u, num_v
     int final_ui_ = 0;      // which (u, v) buffer pair holds the result (fixed by the level count)
 
     cudaGraphExec_t graph_exec_ = nullptr;
-    struct Key { int rows = 0, cols = 0; b2f_brox_params P{}; void *base = nullptr; } key_;
+    struct Key { int rows = 0, cols = 0; b2f_brox_params P{}; EngineKnobs knobs; void *base = nullptr; } key_;
     uint64_t g_launches_ = 0, g_cls_launches_[B2F_MAX_KERNEL_CLASSES] = {};
     double g_cls_bytes_[B2F_MAX_KERNEL_CLASSES] = {};
     int g_iters_ = 0;
@@ -494,6 +763,7 @@ cudaError_t BroxEngine::ensure_workspace(int rows, int cols) {
 void BroxEngine::solve(Ctx &c) {
     const dim3 block(32, 8);
     const size_t sor_smem = sizeof(float) * 11 * SR * SR;
+    const size_t sor_reg_smem = sizeof(float) * 10 * SR * SR;  // two float4 constant arrays + two exchange planes
     const float inv_sf = 1.0f / static_cast<float>(P.scale_factor);  // kernels get 1/xFactor (NS:2264,2270)
     const int nl = static_cast<int>(L_.levels.size());
     // restriction, level by level from the previous one
@@ -524,12 +794,15 @@ void BroxEngine::solve(Ctx &c) {
         T.num_dudv = sp(S_NDUDV, w);
         T.num_u = Plane{extra_[0], plane_pitch(w)};
         T.num_v = Plane{extra_[1], plane_pitch(w)};
+        T.wIz = sp(S_WIZ, w); T.wIx = sp(S_WIX, w); T.wIxz = sp(S_WIXZ, w); T.wIxy = sp(S_WIXY, w);
+        T.wIxx = sp(S_WIXX, w); T.wIy = sp(S_WIY, w); T.wIyz = sp(S_WIYZ, w); T.wIyy = sp(S_WIYY, w);
         Plane dun = sp(S_DUN, w), dvn = sp(S_DVN, w);
 
         fill_plane(c, T.du, h, w, 0.f);
         fill_plane(c, T.dv, h, w, 0.f);
         B2F_LAUNCH(c, CLS_DERIV, 24.0 * npx, k_brox_deriv1, grid, block, 0, T.I0, T.I1, T.Ix0, T.Iy0, T.Ix, T.Iy, h, w);
         B2F_LAUNCH(c, CLS_DERIV, 20.0 * npx, k_brox_deriv2, grid, block, 0, T.Ix, T.Iy, T.Ixx, T.Iyy, T.Ixy, h, w);
+        B2F_LAUNCH(c, CLS_PREP, 76.0 * npx, k_brox_warp_terms, grid, block, 0, T, h, w);
         for (int in = 0; in < P.inner_iterations; ++in) {
             B2F_LAUNCH(c, CLS_PREP, 104.0 * npx, k_brox_prepare, grid, block, 0, T, h, w, static_cast<float>(P.alpha),
                        static_cast<float>(P.gamma));
@@ -541,16 +814,42 @@ void BroxEngine::solve(Ctx &c) {
                 int left = P.solver_iterations;
                 const bool single = w <= SR && h <= SR;  // whole level in one region: no halo, one launch
                 Plane cdu = T.du, cdv = T.dv, ndu = dun, ndv = dvn;
+                // iterations fused per launch: more iterations = fewer launches but a wider halo (smaller tile,
+                // more CTAs).  Small and mid levels are latency-bound (one wave), so they take all iterations in
+                // one launch; large levels keep the tile big.  Cost model in microseconds: fill ~3, half sweep
+                // ~0.35, launch gap ~2, per wave of 148 CTAs.
+                int it_best = 5;
+                if (!single && knobs.fused_iters > 0) {
+                    it_best = knobs.fused_iters;
+                } else if (!single) {
+                    double best = 1e30;
+                    for (int cand = 1; cand <= 12 && cand <= P.solver_iterations; ++cand) {
+                        const int t = SR - 4 * cand;
+                        if (t < 8) break;
+                        const int launches = div_up(P.solver_iterations, cand);
+                        const double waves = std::ceil((double)div_up(w, t) * div_up(h, t) / 148.0);
+                        const double cost = launches * (waves * (3.0 + 0.7 * cand) + 2.0);
+                        if (cost < best) {
+                            best = cost;
+                            it_best = cand;
+                        }
+                    }
+                }
+                if (it_best > 13) it_best = 13;
                 while (left > 0) {
-                    const int it = single ? left : (left < 5 ? left : 5);
+                    const int it = single ? left : (left < it_best ? left : it_best);
                     const int halo = single ? 0 : 2 * it;
                     const int tile = single ? SR : SR - 2 * halo;
                     const dim3 gs(single ? 1 : div_up(w, tile), single ? 1 : div_up(h, tile));
                     BroxLevelPlanes Q = T;
                     Q.du = cdu;
                     Q.dv = cdv;
-                    B2F_LAUNCH(c, CLS_SOR, 52.0 * npx * it, k_brox_sor_fused_pp, gs, dim3(S_THREADS), sor_smem, Q, ndu, ndv,
-                               h, w, omega, it, halo, tile);
+                    if (knobs.kernel_path == 2)
+                        B2F_LAUNCH(c, CLS_SOR, 52.0 * npx * it, k_brox_sor_fused_pp, gs, dim3(S_THREADS), sor_smem, Q, ndu,
+                                   ndv, h, w, omega, it, halo, tile);
+                    else
+                        B2F_LAUNCH(c, CLS_SOR, 52.0 * npx * it, k_brox_sor_reg, gs, dim3(S_THREADS), sor_reg_smem, Q, ndu,
+                                   ndv, h, w, omega, it, halo, tile);
                     Plane t1 = cdu; cdu = ndu; ndu = t1;
                     Plane t2 = cdv; cdv = ndv; ndv = t2;
                     left -= it;
@@ -592,7 +891,7 @@ int BroxEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
         P.solver_iterations <= 0)
         return B2F_BAD_ARG;
     if (!(P.scale_factor > 0.0 && P.scale_factor < 1.0)) return B2F_BAD_ARG;
-    if (I0->step < (size_t)I0->cols * 4 || I1->step < (size_t)I1->cols * 4 || flow->step < (size_t)flow->cols * 8)
+    if (I0->step < (size_t)I0->cols * 4 || I1->step < (size_t)I1->cols * 4 || !flow_step_ok(flow))
         return B2F_BAD_ARG;
     const int rows = I0->rows, cols = I0->cols;
     Ctx c = make_ctx(s);
@@ -603,6 +902,8 @@ int BroxEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
         if (dev >= 0 && dev < 64 && !attr_done[dev]) {
             c.check(cudaFuncSetAttribute(k_brox_sor_fused_pp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(float) * 11 * SR * SR)));
+            c.check(cudaFuncSetAttribute(k_brox_sor_reg, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(float) * 10 * SR * SR)));
             attr_done[dev] = c.ok();
         }
     }
@@ -619,7 +920,7 @@ int BroxEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
     const bool want_graph = knobs.use_graph && !profiling && s != nullptr;
     if (want_graph) {
         const bool hit = graph_exec_ && key_.rows == rows && key_.cols == cols && std::memcmp(&key_.P, &P, sizeof(P)) == 0 &&
-                         key_.base == L_.levels[0].I0.p;
+                         std::memcmp(&key_.knobs, &knobs, sizeof(knobs)) == 0 && key_.base == L_.levels[0].I0.p;
         if (!hit) {
             destroy_graph();
             cudaStream_t cs = nullptr;
@@ -644,7 +945,7 @@ int BroxEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
                 g_iters_ = scratch.iterations_run;
                 c.check(g.err);
                 if (c.ok()) {
-                    key_.rows = rows; key_.cols = cols; key_.P = P; key_.base = L_.levels[0].I0.p;
+                    key_.rows = rows; key_.cols = cols; key_.P = P; key_.knobs = knobs; key_.base = L_.levels[0].I0.p;
                 } else {
                     destroy_graph();
                 }

@@ -123,6 +123,10 @@ struct b2f_handle {
     bool flow_type_ok(const b2f_image *flow) const {
         return planar_v ? flow->type == B2F_32FC1 : flow->type == B2F_32FC2;
     }
+    bool flow_step_ok(const b2f_image *flow) const {
+        const size_t row = (size_t)flow->cols * (planar_v ? 4 : 8);
+        return flow->step >= row && (!planar_v || planar_v_step >= row);
+    }
     b2f::ImageView flow_view(const b2f_image *flow, int rows, int cols) const {
         b2f::ImageView v{flow->data, flow->step, rows, cols, planar_v ? B2F_32FC1 : B2F_32FC2};
         v.data2 = planar_v;

@@ -810,7 +810,7 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
     if (P.num_levels < 0 || P.num_iters < 0 || P.win_size < 1 || (P.win_size & 1) == 0) return B2F_BAD_ARG;
     if (!(P.pyr_scale > 0.0 && P.pyr_scale < 1.0)) return B2F_BAD_ARG;
     const size_t es = I0->type == B2F_8UC1 ? 1 : 4;
-    if (I0->step < I0->cols * es || I1->step < I1->cols * es || flow->step < (size_t)flow->cols * 8) return B2F_BAD_ARG;
+    if (I0->step < I0->cols * es || I1->step < I1->cols * es || !flow_step_ok(flow)) return B2F_BAD_ARG;
 
     const int rows = I0->rows, cols = I0->cols;
     Ctx c = make_ctx(s);

@@ -200,4 +200,14 @@ int b2f_video_fetch(b2f_video *v, int64_t pair_index, void *host_flow, size_t st
     return B2F_OK;
 }
 
+int b2f_video_fetch_view(b2f_video *v, int64_t pair_index, const float **host_flow, size_t *step) {
+    if (!v || !host_flow || !step || pair_index < 0) return B2F_BAD_ARG;
+    const int slot = static_cast<int>(pair_index % v->depth);
+    if (v->flow_pair[slot] != pair_index) return B2F_BAD_ARG;
+    VCHECK(cudaEventSynchronize(v->down_done[slot]));
+    *host_flow = reinterpret_cast<const float *>(v->h_flow(pair_index));
+    *step = 8 * (size_t)v->cols;
+    return B2F_OK;
+}
+
 }  // extern "C"

@@ -54,7 +54,17 @@ class VideoFlow:
             raise B2FError(st)
         return int(idx.value)
 
-    def fetch(self, pair_index: int, out: np.ndarray | None = None) -> np.ndarray:
+    def fetch(self, pair_index: int, out: np.ndarray | None = None, copy: bool = True) -> np.ndarray:
+        """Wait for a pair's flow.  ``copy=False`` returns a read-only view of the front end's pinned result
+        ring (no 16 MB host copy at 1080p); it stays valid until ``depth`` further frames have been pushed."""
+        if not copy:
+            ptr, step = C.POINTER(C.c_float)(), C.c_size_t()
+            st = self._lib.b2f_video_fetch_view(self._v, pair_index, C.byref(ptr), C.byref(step))
+            if st != 0:
+                raise B2FError(st)
+            a = np.ctypeslib.as_array(ptr, shape=(self.rows, self.cols, 2))
+            a.flags.writeable = False
+            return a
         if out is None:
             out = np.empty((self.rows, self.cols, 2), np.float32)
         st = self._lib.b2f_video_fetch(self._v, pair_index, out.ctypes.data, out.strides[0])
@@ -62,9 +72,10 @@ class VideoFlow:
             raise B2FError(st)
         return out
 
-    def run(self, frames):
+    def run(self, frames, copy: bool = True):
         """Generator: yields (pair_index, flow) for every consecutive pair of ``frames``, keeping
-        ``depth - 1`` pairs in flight."""
+        ``depth - 1`` pairs in flight.  With ``copy=False`` each yielded flow is a view that is only valid
+        until the generator is advanced again."""
         pending = []
         for f in frames:
             p = self.push(f)
@@ -72,6 +83,6 @@ class VideoFlow:
                 pending.append(p)
             while len(pending) >= self.depth:
                 q = pending.pop(0)
-                yield q, self.fetch(q)
+                yield q, self.fetch(q, copy=copy)
         for q in pending:
-            yield q, self.fetch(q)
+            yield q, self.fetch(q, copy=copy)

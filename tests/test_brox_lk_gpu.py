@@ -40,19 +40,23 @@ def test_brox_matches_model(cuda_device, h, w, kind):
     assert alg.getDefaultName() == "DenseOpticalFlow.BroxOpticalFlow"
 
 
-def test_brox_fused_sor_bit_identical_to_half_sweep_kernels(cuda_device):
-    """kernel_path=1 runs one launch per red/black half sweep (the reference's shape); the default path
-    fuses up to 5 iterations per launch in shared memory.  Same arithmetic, same order -> same bits."""
+@pytest.mark.parametrize("h,w,solver", [(150, 203, 7), (61, 64, 10), (300, 417, 10)])
+def test_brox_fused_sor_bit_identical_to_half_sweep_kernels(cuda_device, h, w, solver):
+    """kernel_path=1 runs one launch per red/black half sweep (the reference's shape); path 2 fuses up to 5
+    iterations per launch in shared memory; the default path keeps the cells in registers.  Same arithmetic,
+    same order (brox_sor_cell) -> same bits, including levels that fit one region and odd sizes."""
     import torch
     import opencv_contrib_b200 as ocb
-    I0, I1, _ = synth.make_pair(150, 203, seed=7, kind="smooth", dtype="f32")
+    I0, I1, _ = synth.make_pair(h, w, seed=7, kind="smooth", dtype="f32")
     d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
     outs = []
-    for path in (0, 1):
-        alg = ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, 3, 77, 7)
+    for path in (0, 1, 2):
+        alg = ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, 3, 77, solver)
         alg.setEngineOption("kernel_path", path)
         outs.append(alg.calc(d0, d1).cpu().numpy())
+    assert np.isfinite(outs[0]).all()
     assert np.array_equal(outs[0], outs[1]), float(np.abs(outs[0] - outs[1]).max())
+    assert np.array_equal(outs[2], outs[1]), float(np.abs(outs[2] - outs[1]).max())
 
 
 def test_brox_reference_test_parameters_recover_motion(cuda_device):
@@ -121,3 +125,19 @@ def test_denselk_recovers_motion_and_rejects_bad_args(cuda_device):
     with pytest.raises(ocb.B2FError) as e:
         ocb.DensePyrLKOpticalFlow_create(winSize=(2, 13)).calc(a.to(torch.uint8), a.to(torch.uint8))
     assert e.value.status == 1                           # winSize > 2 (pyrlk.cpp:243)
+
+
+@pytest.mark.parametrize("win_h,levels", [(13, 3), (7, 1)])
+def test_denselk_fast_kernel_bit_identical_to_generic(cuda_device, win_h, levels):
+    """Window width 13 takes the kernel that hoists the x half of every bilinear fetch into registers
+    (kernel_path 0); kernel_path 1 forces the generic per-tap kernel.  Same arithmetic per tap."""
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(131, 177, seed=9, kind="smooth")
+    d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
+    outs = []
+    for path in (0, 1):
+        alg = ocb.DensePyrLKOpticalFlow_create(winSize=(13, win_h), maxLevel=levels, iters=12)
+        alg.setEngineOption("kernel_path", path)
+        outs.append(alg.calc(d0, d1, torch.zeros((131, 177, 2), device=cuda_device)).cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]), float(np.abs(outs[0] - outs[1]).max())
