@@ -443,88 +443,55 @@ struct SorRegs {
     float du, dv, U, V, u, v, usum, vsum, w_v;
 };
 
+// No border logic is needed inside the sweep: wherever the reference clamps a neighbour index (image border) the
+// matching diffusivity is zero (sx = 0 at i = 0, sy = 0 at j = 0 by construction; s_right / s_up are zeroed
+// at the far edges on load), so the clamped neighbour contributes exactly +-0 whatever finite value is read;
+// cells outside the image carry all-zero constants and therefore stay at du = dv = 0.
 template <int CP0>
 __device__ __forceinline__ void brox_half_sweep(SorRegs (&c)[4][2], const float4 *__restrict__ sS,
                                                 const float4 *__restrict__ sN, float *__restrict__ xU,
-                                                float *__restrict__ xV, int lane, int ry0, int rx0, int gx0, int gy0,
-                                                int w, int h, float one_minus_omega) {
+                                                float *__restrict__ xV, int lane, int ry0, int rx0,
+                                                float one_minus_omega) {
     // neighbours across the 4-row boundary (the other colour: written in the previous half sweep)
-    const int cpT = CP0, cpB = CP0 ^ 1;  // active column in patch rows 0 and 3
+    constexpr int cpT = CP0, cpB = CP0 ^ 1;  // active column in patch rows 0 and 3
     const int below = (ry0 > 0 ? ry0 - 1 : ry0) * SR + rx0 + cpT;
     const int above = (ry0 + 4 < SR ? ry0 + 4 : ry0 + 3) * SR + rx0 + cpB;
     const float Ud0 = xU[below], Vd0 = xV[below];
     const float Uu3 = xU[above], Vu3 = xV[above];
+    const float4 *pS = sS + (ry0 * 2) * 32 + lane, *pN = sN + (ry0 * 2) * 32 + lane;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         constexpr int dummy = 0;
         (void)dummy;
         const int cp = (CP0 ^ r) & 1;  // compile-time after unrolling
-        const int gy = gy0 + ry0 + r, gx = gx0 + rx0 + cp;
-        // horizontal neighbours: the other column of the own patch, or the adjacent lane's
+        // horizontal neighbours: the other column of the own patch and the adjacent lane's (a region-edge lane
+        // gets its own value back from the shuffle: stale but finite, and it lies in the halo)
         const float Uo = c[r][cp ^ 1].U, Vo = c[r][cp ^ 1].V;
-        float Ux, Vx;  // value from the neighbouring lane
-        if (cp == 0) {
-            Ux = __shfl_up_sync(0xffffffffu, Uo, 1);
-            Vx = __shfl_up_sync(0xffffffffu, Vo, 1);
-        } else {
-            Ux = __shfl_down_sync(0xffffffffu, Uo, 1);
-            Vx = __shfl_down_sync(0xffffffffu, Vo, 1);
-        }
-        SorRegs &me = c[r][cp];
-        const bool active = gx >= 0 && gy >= 0 && gx < w && gy < h;
         float Ul, Ur, Vl, Vr;
         if (cp == 0) {
-            const bool edge = lane == 0 || gx <= 0;
-            Ul = edge ? me.U : Ux;
-            Vl = edge ? me.V : Vx;
-            const bool redge = gx >= w - 1;
-            Ur = redge ? me.U : Uo;
-            Vr = redge ? me.V : Vo;
+            Ul = __shfl_up_sync(0xffffffffu, Uo, 1);
+            Vl = __shfl_up_sync(0xffffffffu, Vo, 1);
+            Ur = Uo;
+            Vr = Vo;
         } else {
-            const bool edge = gx <= 0;
-            Ul = edge ? me.U : Uo;
-            Vl = edge ? me.V : Vo;
-            const bool redge = lane == 31 || gx >= w - 1;
-            Ur = redge ? me.U : Ux;
-            Vr = redge ? me.V : Vx;
+            Ur = __shfl_down_sync(0xffffffffu, Uo, 1);
+            Vr = __shfl_down_sync(0xffffffffu, Vo, 1);
+            Ul = Uo;
+            Vl = Vo;
         }
-        float Ud, Vd, Uu, Vu;
-        if (r == 0) {
-            Ud = Ud0;
-            Vd = Vd0;
-        } else {
-            Ud = c[r > 0 ? r - 1 : 0][cp].U;
-            Vd = c[r > 0 ? r - 1 : 0][cp].V;
-        }
-        if (r == 3) {
-            Uu = Uu3;
-            Vu = Vu3;
-        } else {
-            Uu = c[r < 3 ? r + 1 : 3][cp].U;
-            Vu = c[r < 3 ? r + 1 : 3][cp].V;
-        }
-        if (gy <= 0 || (r == 0 && ry0 == 0)) {
-            Ud = me.U;
-            Vd = me.V;
-        }
-        if (gy >= h - 1 || (r == 3 && ry0 + 4 == SR)) {
-            Uu = me.U;
-            Vu = me.V;
-        }
-        const int slot = ((ry0 + r) * 2 + cp) * 32 + lane;
-        const float4 S = sS[slot], N = sN[slot];
+        const float Ud = r == 0 ? Ud0 : c[r > 0 ? r - 1 : 0][cp].U;
+        const float Vd = r == 0 ? Vd0 : c[r > 0 ? r - 1 : 0][cp].V;
+        const float Uu = r == 3 ? Uu3 : c[r < 3 ? r + 1 : 3][cp].U;
+        const float Vu = r == 3 ? Vu3 : c[r < 3 ? r + 1 : 3][cp].V;
+        SorRegs &me = c[r][cp];
+        const float4 S = pS[(r * 2 + cp) * 32], N = pN[(r * 2 + cp) * 32];
         SorConst k;
         k.s_l = S.x; k.s_r = S.y; k.s_u = S.z; k.s_d = S.w;
         k.num_u = N.x; k.num_v = N.y; k.num_dudv = N.z; k.w_u = N.w;
         k.usum = me.usum; k.vsum = me.vsum; k.w_v = me.w_v;
-        float du = me.du, dv = me.dv;
-        brox_sor_cell(k, Ul, Uu, Ur, Ud, Vl, Vu, Vr, Vd, one_minus_omega, du, dv);
-        if (active) {
-            me.du = du;
-            me.dv = dv;
-            me.U = __fadd_rn(me.u, du);
-            me.V = __fadd_rn(me.v, dv);
-        }
+        brox_sor_cell(k, Ul, Uu, Ur, Ud, Vl, Vu, Vr, Vd, one_minus_omega, me.du, me.dv);
+        me.U = __fadd_rn(me.u, me.du);
+        me.V = __fadd_rn(me.v, me.dv);
     }
     // publish the updated boundary cells for the neighbouring warps' next half sweep
     xU[ry0 * SR + rx0 + cpT] = c[0][cpT].U;
@@ -590,11 +557,16 @@ __global__ void __launch_bounds__(S_THREADS, 1)
     // colour 0 first (sor_pass<0>, NB:915-922): cells with (gx + gy) even; gx0 is even, so in patch row 0 the
     // active column is (colour ^ gy0 ^ ry0) & 1 = (colour ^ gy0) & 1 -- uniform over the CTA
     const int par = gy0 & 1;
+    // warps whose four rows lie outside the image hold only zero cells: they skip the arithmetic (small levels
+    // occupy a corner of the region) but keep the barrier
+    const bool live = gy0 + ry0 < h && gy0 + ry0 + 3 >= 0;
     for (int sweep = 0; sweep < 2 * iters; ++sweep) {
-        if (((sweep ^ par) & 1) == 0)
-            brox_half_sweep<0>(c, sS, sN, xU, xV, lane, ry0, rx0, gx0, gy0, w, h, omo);
-        else
-            brox_half_sweep<1>(c, sS, sN, xU, xV, lane, ry0, rx0, gx0, gy0, w, h, omo);
+        if (live) {
+            if (((sweep ^ par) & 1) == 0)
+                brox_half_sweep<0>(c, sS, sN, xU, xV, lane, ry0, rx0, omo);
+            else
+                brox_half_sweep<1>(c, sS, sN, xU, xV, lane, ry0, rx0, omo);
+        }
         __syncthreads();
     }
 

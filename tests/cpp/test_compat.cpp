@@ -86,7 +86,9 @@ int main(int argc, char **argv) {
         hu.upload(nu.data(), hs, stream);
         hv.upload(nv.data(), hs, stream);
         try {
-            cvcuda::interpolateFrames(g0, g1, gu, gv, hu, hv, 0.5f, mid, buf, stream);
+            // corrected mode: the reference mode's coverage-clear defect depends on the GpuMat pitch (cudaMallocPitch pads
+            // 168 floats to 256), which the Python call site (contiguous tensors) does not share
+            cvcuda::interpolateFrames(g0, g1, gu, gv, hu, hv, 0.5f, mid, buf, stream, true);
         } catch (const std::exception &e) {
             fprintf(stderr, "exception: %s\n", e.what());
             return 6;
