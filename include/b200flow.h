@@ -258,6 +258,31 @@ B2F_API int b2f_video_fetch(b2f_video *v, int64_t pair_index, void *host_flow, s
 B2F_API int b2f_video_fetch_view(b2f_video *v, int64_t pair_index, const float **host_flow, size_t *step);
 B2F_API void b2f_video_destroy(b2f_video *v);
 
+/* ---- cv::cuda::SparsePyrLKOpticalFlow (cudaoptflow.hpp:189-226; src/pyrlk.cpp:153-236,344-376;
+ *      src/cuda/pyrlk.cu:148-345): pyramidal Lucas-Kanade for a list of points.  Images: device CV_8UC1 or
+ *      CV_32FC1 (the reference additionally instantiates 16U / 32S and 3 / 4 channels: not built here).
+ *      prev_pts / next_pts: device arrays of n_points interleaved (x, y) float32 -- the reference's 1 x N
+ *      CV_32FC2 GpuMat; status: n_points bytes (1 = tracked); err: n_points float32 or NULL.  next_pts is
+ *      read first only when use_initial_flow is set.  A point that leaves the image or whose 2x2 matrix is
+ *      singular keeps the coordinates of the last level that updated it and gets status 0 on level 0,
+ *      exactly as the reference kernel returns early (pyrlk.cu:162-168,232-238,256-262). ---- */
+typedef struct b2f_sparselk_params {
+    int win_width;        /* 21 */
+    int win_height;       /* 21 */
+    int max_level;        /* 3  */
+    int iters;            /* 30 */
+    int use_initial_flow; /* 0  */
+} b2f_sparselk_params;
+typedef struct b2f_sparse b2f_sparse;
+B2F_API void b2f_sparselk_default_params(b2f_sparselk_params *p);
+B2F_API int b2f_sparselk_create(const b2f_sparselk_params *p, b2f_sparse **out);
+B2F_API int b2f_sparselk_set_params(b2f_sparse *h, const b2f_sparselk_params *p);
+B2F_API int b2f_sparselk_get_params(const b2f_sparse *h, b2f_sparselk_params *p);
+B2F_API int b2f_sparselk_calc(b2f_sparse *h, const b2f_image *prev_img, const b2f_image *next_img,
+                              const float *prev_pts, float *next_pts, unsigned char *status, float *err,
+                              int n_points, void *cuda_stream);
+B2F_API void b2f_sparselk_destroy(b2f_sparse *h);
+
 /* ---- Middlebury .flo files and the reference's error measures (host side).
  *      Format: float tag 202021.25 ("PIEH"), int32 width, int32 height, then rows of interleaved
  *      (u, v) float32 (optflow/test/test_tvl1optflow.cpp:49-108,

@@ -238,6 +238,55 @@ public:
 
 #undef B2F_ACCESSOR
 
+/** cv::cuda::SparsePyrLKOpticalFlow (cudaoptflow.hpp:189-226).  prevPts / nextPts are 1 x N CV_32FC2, status
+ *  1 x N CV_8UC1, err 1 x N CV_32FC1; nextPts, status and err are (re)allocated like the reference does
+ *  (pyrlk.cpp:165,172,176).  `err` is a pointer here (nullptr = cv::noArray()). */
+class SparsePyrLKOpticalFlow : public Algorithm {
+public:
+    ~SparsePyrLKOpticalFlow() { b2f_sparselk_destroy(h_); }
+    void calc(const GpuMat &prevImg, const GpuMat &nextImg, const GpuMat &prevPts, GpuMat &nextPts, GpuMat &status,
+              GpuMat *err = nullptr, Stream &stream = Stream::Null()) {
+        if (prevPts.cols == 0) return;
+        if (prevPts.rows != 1 || prevPts.type() != 13 /*CV_32FC2*/) detail::fail(B2F_BAD_ARG, "SparsePyrLKOpticalFlow::calc");
+        if (!getUseInitialFlow()) nextPts.create(1, prevPts.cols, 13);
+        else if (nextPts.cols != prevPts.cols || nextPts.type() != 13) detail::fail(B2F_SIZE_MISMATCH, "SparsePyrLKOpticalFlow::calc");
+        status.create(1, prevPts.cols, 0 /*CV_8UC1*/);
+        if (err) err->create(1, prevPts.cols, 5 /*CV_32FC1*/);
+        b2f_image i0{prevImg.data, prevImg.step, prevImg.rows, prevImg.cols, prevImg.type()};
+        b2f_image i1{nextImg.data, nextImg.step, nextImg.rows, nextImg.cols, nextImg.type()};
+        const int st = b2f_sparselk_calc(h_, &i0, &i1, reinterpret_cast<const float *>(prevPts.data),
+                                         reinterpret_cast<float *>(nextPts.data), reinterpret_cast<unsigned char *>(status.data),
+                                         err ? reinterpret_cast<float *>(err->data) : nullptr, prevPts.cols, detail::raw(stream));
+        if (st != B2F_OK) detail::fail(st, "SparsePyrLKOpticalFlow::calc");
+    }
+    Size getWinSize() const { const auto p = params(); return Size(p.win_width, p.win_height); }
+    void setWinSize(Size s) { auto p = params(); p.win_width = s.width; p.win_height = s.height; b2f_sparselk_set_params(h_, &p); }
+    int getMaxLevel() const { return params().max_level; }
+    void setMaxLevel(int v) { auto p = params(); p.max_level = v; b2f_sparselk_set_params(h_, &p); }
+    int getNumIters() const { return params().iters; }
+    void setNumIters(int v) { auto p = params(); p.iters = v; b2f_sparselk_set_params(h_, &p); }
+    bool getUseInitialFlow() const { return params().use_initial_flow != 0; }
+    void setUseInitialFlow(bool v) { auto p = params(); p.use_initial_flow = v; b2f_sparselk_set_params(h_, &p); }
+    String getDefaultName() const override { return "SparseOpticalFlow.SparsePyrLKOpticalFlow"; }
+
+    static Ptr<SparsePyrLKOpticalFlow> create(Size winSize = Size(21, 21), int maxLevel = 3, int iters = 30,
+                                              bool useInitialFlow = false) {
+        b2f_sparselk_params p{winSize.width, winSize.height, maxLevel, iters, useInitialFlow};
+        auto o = detail::make<SparsePyrLKOpticalFlow>();
+        const int st = b2f_sparselk_create(&p, &o->h_);
+        if (st != B2F_OK) detail::fail(st, "SparsePyrLKOpticalFlow::create");
+        return o;
+    }
+
+private:
+    b2f_sparse *h_ = nullptr;
+    b2f_sparselk_params params() const {
+        b2f_sparselk_params p{};
+        b2f_sparselk_get_params(h_, &p);
+        return p;
+    }
+};
+
 /** cv::cuda::interpolateFrames (cudalegacy.hpp:229, src/interpolate_frames.cpp:54-111): same argument order;
  *  newFrame and buf are (re)allocated like the reference does (:64-67).  `corrected` = false keeps the
  *  reference's behaviour including its defects (see b200flow.h). */

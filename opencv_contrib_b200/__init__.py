@@ -21,6 +21,8 @@ from .cudaoptflow import (  # noqa: F401
     FarnebackOpticalFlow_create,
     BroxOpticalFlow_create,
     DensePyrLKOpticalFlow_create,
+    SparsePyrLKOpticalFlow,
+    SparsePyrLKOpticalFlow_create,
     OPTFLOW_USE_INITIAL_FLOW,
     OPTFLOW_FARNEBACK_GAUSSIAN,
 )

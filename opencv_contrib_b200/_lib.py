@@ -49,6 +49,11 @@ class b2f_denselk_params(C.Structure):
                 ("iters", C.c_int), ("use_initial_flow", C.c_int)]
 
 
+class b2f_sparselk_params(C.Structure):
+    _fields_ = [("win_width", C.c_int), ("win_height", C.c_int), ("max_level", C.c_int), ("iters", C.c_int),
+                ("use_initial_flow", C.c_int)]
+
+
 class b2f_stats(C.Structure):
     _fields_ = [("calls", C.c_uint64), ("launches", C.c_uint64),
                 ("class_launches", C.c_uint64 * B2F_MAX_KERNEL_CLASSES),
@@ -98,6 +103,13 @@ SYMBOLS = [
     ("b2f_video_fetch", C.c_int, [_H, C.c_int64, C.c_void_p, C.c_size_t]),
     ("b2f_video_fetch_view", C.c_int, [_H, C.c_int64, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_size_t)]),
     ("b2f_video_destroy", None, [_H]),
+    ("b2f_sparselk_default_params", None, [C.POINTER(b2f_sparselk_params)]),
+    ("b2f_sparselk_create", C.c_int, [C.POINTER(b2f_sparselk_params), C.POINTER(_H)]),
+    ("b2f_sparselk_set_params", C.c_int, [_H, C.POINTER(b2f_sparselk_params)]),
+    ("b2f_sparselk_get_params", C.c_int, [_H, C.POINTER(b2f_sparselk_params)]),
+    ("b2f_sparselk_calc", C.c_int, [_H, _IMG, _IMG, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p]),
+    ("b2f_sparselk_destroy", None, [_H]),
     ("b2f_flo_read_size", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("b2f_flo_read", C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     ("b2f_flo_write", C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),

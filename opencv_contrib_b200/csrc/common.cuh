@@ -169,6 +169,8 @@ void split_flow(Ctx &c, int cls, const ImageView &flow, Plane u, Plane v);
 void fill_plane(Ctx &c, Plane p, int rows, int cols, float value_bits_zero_only);
 // cv::cuda::pyrDown f32 C1 (cudawarping/src/cuda/pyr_down.cu:55-173): 5x5 [1 4 6 4 1]/16, REFLECT101.
 void pyr_down(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, int drows, int dcols);
+// same for an 8-bit pyramid held in float planes: the result is rounded like saturate_cast<uchar> (pyr_down.cu:172)
+void pyr_down_u8(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, int drows, int dcols);
 
 // resize.cpp:76-84 scale rule: scale passed to the kernel is float(1/f).
 static inline float inv_scale_from_sizes(int src, int dst) { return static_cast<float>(1.0 / (static_cast<double>(dst) / src)); }

@@ -96,6 +96,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // cv::cuda::pyrDown (cudawarping/src/cuda/pyr_down.cu:55-173): horizontal 5-tap [1 4 6 4 1] on the
 // five source rows 2y-2..2y+2 (reflect101), then vertical 5-tap, /256.  Same operation order:
 // row sums first (sum over the 5 rows weighted), then across columns, scaled by 1/256 at the end.
+template <bool ROUND_U8>
 __global__ void k_pyr_down(Plane s, int srows, int scols, Plane d, int drows, int dcols) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -124,6 +125,8 @@ __global__ void k_pyr_down(Plane s, int srows, int scols, Plane d, int drows, in
     out = out + 0.375f * col[2];
     out = out + 0.25f * col[3];
     out = out + 0.0625f * col[4];
+    // 8-bit pyramids: saturate_cast<uchar>(sum) rounds half to even (pyr_down.cu:172)
+    if (ROUND_U8) out = rintf(fminf(fmaxf(out, 0.f), 255.f));
     d.at(y, x) = out;
 }
 
@@ -214,7 +217,14 @@ void fill_plane(Ctx &c, Plane p, int rows, int cols, float) {
 void pyr_down(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, int drows, int dcols) {
     const dim3 block(32, 8);
     const dim3 grid = grid2d(dcols, drows, 1);
-    B2F_LAUNCH(c, cls, 4.0 * ((double)srows * scols + (double)drows * dcols), k_pyr_down, grid, block, 0, s, srows,
+    B2F_LAUNCH(c, cls, 4.0 * ((double)srows * scols + (double)drows * dcols), k_pyr_down<false>, grid, block, 0, s, srows,
+               scols, d, drows, dcols);
+}
+
+void pyr_down_u8(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, int drows, int dcols) {
+    const dim3 block(32, 8);
+    const dim3 grid = grid2d(dcols, drows, 1);
+    B2F_LAUNCH(c, cls, 4.0 * ((double)srows * scols + (double)drows * dcols), k_pyr_down<true>, grid, block, 0, s, srows,
                scols, d, drows, dcols);
 }
 

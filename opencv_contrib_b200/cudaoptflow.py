@@ -269,3 +269,98 @@ def DensePyrLKOpticalFlow_create(winSize=(13, 13), maxLevel=3, iters=30, useInit
     """cv::cuda::DensePyrLKOpticalFlow::create (cudaoptflow.hpp:245-249)."""
     p = _lib.b2f_denselk_params(winSize[0], winSize[1], maxLevel, iters, int(useInitialFlow))
     return _create(DensePyrLKOpticalFlow, "b2f_denselk_create", p)
+
+
+class SparsePyrLKOpticalFlow:
+    """cv::cuda::SparsePyrLKOpticalFlow (cudaoptflow.hpp:189-226).
+
+        nextPts, status, err = alg.calc(prevImg, nextImg, prevPts[, nextPts[, status[, err[, stream]]]])
+
+    prevPts / nextPts: CUDA float32 tensors of shape (1, N, 2) or (N, 2) (the reference's 1 x N CV_32FC2 GpuMat),
+    status: uint8 (N,), err: float32 (N,) -- computed only when ``err`` is passed or ``wantErr=True``.
+    """
+
+    def __init__(self, handle):
+        self._h = handle
+        self._lib = _lib.lib()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.b2f_sparselk_destroy(h)
+
+    def _params(self):
+        p = _lib.b2f_sparselk_params()
+        self._lib.b2f_sparselk_get_params(self._h, C.byref(p))
+        return p
+
+    def _update(self, **kw):
+        p = self._params()
+        for k, v in kw.items():
+            setattr(p, k, int(v))
+        self._lib.b2f_sparselk_set_params(self._h, C.byref(p))
+
+    def getWinSize(self):
+        p = self._params()
+        return (p.win_width, p.win_height)
+
+    def setWinSize(self, sz):
+        self._update(win_width=sz[0], win_height=sz[1])
+
+    def getMaxLevel(self):
+        return self._params().max_level
+
+    def setMaxLevel(self, v):
+        self._update(max_level=v)
+
+    def getNumIters(self):
+        return self._params().iters
+
+    def setNumIters(self, v):
+        self._update(iters=v)
+
+    def getUseInitialFlow(self):
+        return bool(self._params().use_initial_flow)
+
+    def setUseInitialFlow(self, v):
+        self._update(use_initial_flow=bool(v))
+
+    def getDefaultName(self) -> str:
+        return "SparseOpticalFlow.SparsePyrLKOpticalFlow"
+
+    def calc(self, prevImg, nextImg, prevPts, nextPts=None, status=None, err=None, stream=None, wantErr=False):
+        torch = _torch()
+        if prevPts.dtype != torch.float32 or prevPts.shape[-1] != 2 or not prevPts.is_contiguous():
+            raise B2FError(2)  # CV_Assert(prevPts.rows == 1 && prevPts.type() == CV_32FC2), pyrlk.cpp:159
+        n = prevPts.numel() // 2
+        if nextPts is None:
+            if self.getUseInitialFlow():
+                raise B2FError(1)  # CV_Assert(nextPts.size() == prevPts.size()), pyrlk.cpp:162-163
+            nextPts = torch.empty_like(prevPts)
+        elif nextPts.shape != prevPts.shape or nextPts.dtype != torch.float32 or not nextPts.is_contiguous():
+            raise B2FError(3)
+        if status is None:
+            status = torch.empty((n,), dtype=torch.uint8, device=prevPts.device)
+        if err is None and wantErr:
+            err = torch.empty((n,), dtype=torch.float32, device=prevPts.device)
+        i0, i1 = _image_from_tensor(prevImg), _image_from_tensor(nextImg)
+        if stream is None:
+            stream = torch.cuda.current_stream(prevImg.device)
+        sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        st = self._lib.b2f_sparselk_calc(self._h, C.byref(i0), C.byref(i1), C.c_void_p(prevPts.data_ptr()),
+                                         C.c_void_p(nextPts.data_ptr()), C.c_void_p(status.data_ptr()),
+                                         C.c_void_p(err.data_ptr()) if err is not None else None, n, C.c_void_p(sptr))
+        if st != 0:
+            raise B2FError(st)
+        return nextPts, status, err
+
+
+def SparsePyrLKOpticalFlow_create(winSize=(21, 21), maxLevel=3, iters=30, useInitialFlow=False):
+    """cv::cuda::SparsePyrLKOpticalFlow::create (cudaoptflow.hpp:221-225)."""
+    p = _lib.b2f_sparselk_params(winSize[0], winSize[1], maxLevel, iters, int(useInitialFlow))
+    l = _lib.lib()
+    h = C.c_void_p()
+    st = l.b2f_sparselk_create(C.byref(p), C.byref(h))
+    if st != 0:
+        raise B2FError(st)
+    return SparsePyrLKOpticalFlow(h)

@@ -101,6 +101,27 @@ int main(int argc, char **argv) {
         fwrite(m.data(), 4, m.size(), g);
         fclose(g);
     }
+    if (argc >= 8) {
+        // the sparse sibling through the same adapter: three interior points must be tracked
+        const float pts[6] = {cols * 0.5f, rows * 0.5f, cols * 0.25f, rows * 0.6f, cols * 0.7f, rows * 0.3f};
+        cvcuda::GpuMat dp(1, 3, 13 /*CV_32FC2*/), dn, ds, de;
+        dp.upload(pts, sizeof(pts), stream);
+        try {
+            auto sp = cvcuda::SparsePyrLKOpticalFlow::create();
+            if (sp->getWinSize().width != 21 || sp->getMaxLevel() != 3 || sp->getNumIters() != 30) return 8;
+            sp->calc(d0, d1, dp, dn, ds, &de, stream);
+        } catch (const std::exception &e) {
+            fprintf(stderr, "exception: %s\n", e.what());
+            return 9;
+        }
+        unsigned char st[3] = {0, 0, 0};
+        float np[6];
+        ds.download(st, 3, stream);
+        dn.download(np, sizeof(np), stream);
+        stream.waitForCompletion();
+        if (dn.cols != 3 || ds.cols != 3 || de.cols != 3 || !(st[0] && st[1] && st[2])) return 10;
+        printf("sparse %.2f %.2f\n", np[0] - pts[0], np[1] - pts[1]);
+    }
     printf("ok %d %d type=%d step=%zu\n", flow.rows, flow.cols, flow.type(), flow.step);
     return 0;
 }

@@ -1,0 +1,86 @@
+"""GPU tests for SparsePyrLKOpticalFlow through the C ABI.
+
+Oracle: the live CPU reference ``cv2.calcOpticalFlowPyrLK`` with the reference's own acceptance criterion
+(modules/cudaoptflow/test/test_optflow.cpp:188-267): points from goodFeaturesToTrack(1000, 0.01, 0.0), a point
+counts as a mismatch when the status differs or the integer coordinates differ by more than one pixel, and at
+most 1 % of the points may mismatch.
+"""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mismatch(next_gpu, status_gpu, next_cpu, status_cpu):
+    bad = 0
+    for a, sa, b, sb in zip(next_gpu, status_gpu, next_cpu, status_cpu):
+        if bool(sa) != bool(sb):
+            bad += 1
+        elif sa:
+            ai, bi = a.astype(np.int32), b.astype(np.int32)  # cv::Point2i a = nextPts[i] truncates
+            if abs(int(ai[0]) - int(bi[0])) > 1 or abs(int(ai[1]) - int(bi[1])) > 1:
+                bad += 1
+    return bad / max(len(next_gpu), 1)
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+@pytest.mark.parametrize("kind", ["const", "affine"])
+def test_sparse_pyrlk_meets_the_reference_criterion(cuda_device, dtype, kind):
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, gt = synth.make_pair(360, 480, seed=21, kind=kind)
+    pts = cv2.goodFeaturesToTrack(I0, 1000, 0.01, 0.0).reshape(-1, 2).astype(np.float32)
+    assert len(pts) > 300
+    gold, st_gold, _ = cv2.calcOpticalFlowPyrLK(I0, I1, pts.reshape(-1, 1, 2), None)  # reference defaults 21x21, 3
+    gold, st_gold = gold.reshape(-1, 2), st_gold.ravel()
+    conv = (lambda a: a) if dtype == "u8" else (lambda a: a.astype(np.float32))
+    d0, d1 = torch.from_numpy(conv(I0)).to(cuda_device), torch.from_numpy(conv(I1)).to(cuda_device)
+    alg = ocb.SparsePyrLKOpticalFlow_create()
+    assert alg.getWinSize() == (21, 21) and alg.getMaxLevel() == 3 and alg.getNumIters() == 30
+    nxt, status, err = alg.calc(d0, d1, torch.from_numpy(pts).to(cuda_device).reshape(1, -1, 2), wantErr=True)
+    torch.cuda.synchronize()
+    nxt, status, err = nxt.cpu().numpy().reshape(-1, 2), status.cpu().numpy(), err.cpu().numpy()
+    ratio = _mismatch(nxt, status, gold, st_gold)
+    assert ratio <= 0.01, ratio
+    ok = (status != 0) & (st_gold != 0)
+    # tracked points follow the synthetic motion (I0(x) = I1(x + flow))
+    g = gt[np.clip(pts[:, 1].astype(int), 0, 359), np.clip(pts[:, 0].astype(int), 0, 479)]
+    d = np.linalg.norm((nxt - pts) - g, axis=1)[ok]
+    assert np.median(d) < 0.1, float(np.median(d))
+    assert np.isfinite(err[ok]).all() and (err[ok] >= 0).all() and float(np.median(err[ok])) < 10.0
+
+
+def test_sparse_pyrlk_edge_cases(cuda_device):
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(200, 260, seed=5, kind="const")
+    d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
+    alg = ocb.SparsePyrLKOpticalFlow_create(winSize=(15, 11), maxLevel=2, iters=20)
+    pts = np.array([[130.5, 100.25], [-5.0, 50.0], [300.0, 10.0], [259.0, 199.0], [64.0, 64.0]], np.float32)
+    nxt, status, _ = alg.calc(d0, d1, torch.from_numpy(pts).to(cuda_device))
+    status = status.cpu().numpy()
+    assert status[0] == 1 and status[4] == 1
+    assert status[1] == 0 and status[2] == 0          # outside the image: pyrlk.cu:162-168
+    again, st2, _ = alg.calc(d0, d1, torch.from_numpy(pts).to(cuda_device))
+    assert torch.equal(again, nxt) and torch.equal(st2.cpu(), torch.from_numpy(status))  # deterministic
+    # constant image: singular matrix -> status 0 (pyrlk.cu:232-238)
+    flat = torch.full((200, 260), 77, dtype=torch.uint8, device=cuda_device)
+    _, st3, _ = alg.calc(flat, flat, torch.from_numpy(pts[:1]).to(cuda_device))
+    assert int(st3[0]) == 0
+    # use_initial_flow: starting from the answer converges to the same place
+    alg.setUseInitialFlow(True)
+    warm, st4, _ = alg.calc(d0, d1, torch.from_numpy(pts[[0, 4]]).to(cuda_device), nxt[[0, 4]].clone())
+    assert torch.allclose(warm, nxt[[0, 4]], atol=0.05) and bool((st4 == 1).all())
+    with pytest.raises(ocb.B2FError):
+        alg.calc(d0, d1, torch.from_numpy(pts).to(cuda_device))          # nextPts required with useInitialFlow
+    alg.setUseInitialFlow(False)
+    with pytest.raises(ocb.B2FError):
+        alg.calc(d0, d1.float(), torch.from_numpy(pts).to(cuda_device))  # type mismatch (pyrlk.cpp:229)
+    with pytest.raises(ocb.B2FError):
+        ocb.SparsePyrLKOpticalFlow_create(winSize=(2, 21)).calc(d0, d1, torch.from_numpy(pts).to(cuda_device))
+    # empty input -> empty output, no error (pyrlk.cpp:221-227)
+    e, s, _ = alg.calc(d0, d1, torch.empty((0, 2), dtype=torch.float32, device=cuda_device))
+    assert e.numel() == 0 and s.numel() == 0
