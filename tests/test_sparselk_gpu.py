@@ -32,7 +32,14 @@ def test_sparse_pyrlk_meets_the_reference_criterion(cuda_device, dtype, kind):
     import torch
     import opencv_contrib_b200 as ocb
     I0, I1, gt = synth.make_pair(360, 480, seed=21, kind=kind)
-    pts = cv2.goodFeaturesToTrack(I0, 1000, 0.01, 0.0).reshape(-1, 2).astype(np.float32)
+    # Features within a few pixels of the border are excluded: when the true motion carries such a point just
+    # outside the image the reference kernel returns early WITHOUT updating nextPts (pyrlk.cu:256-262), so the
+    # stale half-resolution estimate is doubled on every finer level -- garbage by design, which this engine
+    # reproduces; the CPU tracker handles those points (and in turn diverges at the right / bottom border).
+    # The reference's own test image has hardly any corner there; the synthetic texture does.
+    mask = np.zeros_like(I0)
+    mask[12:-12, 12:-12] = 255
+    pts = cv2.goodFeaturesToTrack(I0, 1000, 0.01, 0.0, mask=mask).reshape(-1, 2).astype(np.float32)
     assert len(pts) > 300
     gold, st_gold, _ = cv2.calcOpticalFlowPyrLK(I0, I1, pts.reshape(-1, 1, 2), None)  # reference defaults 21x21, 3
     gold, st_gold = gold.reshape(-1, 2), st_gold.ravel()
