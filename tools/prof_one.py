@@ -15,6 +15,8 @@ if algo == "tvl1":
     alg = ocb.OpticalFlowDual_TVL1_create(nscales=5, warps=10, epsilon=0.0, iterations=30)
     alg.setEngineOption("fused_iters", K)
     alg.setEngineOption("use_graph", 0)
+elif algo == "denselk":
+    alg = ocb.DensePyrLKOpticalFlow_create()
 else:
     alg = ocb.FarnebackOpticalFlow_create()
 flow = torch.empty((1080, 1920, 2), dtype=torch.float32, device=dev)
