@@ -87,6 +87,16 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def sample_now(self):
+        """One synchronous query (used while work is still queued on the GPU, so short timed regions -- a few
+        Farneback steps finish faster than the 200 ms polling period -- still get a sample under load)."""
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            self.lines.extend(l.strip() for l in out.splitlines() if l.strip())
+        except Exception:
+            pass
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -149,10 +159,12 @@ def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 
         P = tvl1_cpu.TVL1Params(tau=0.25, lambda_=0.15, theta=0.3, nscales=5, warps=10, epsilon=0.0,
                                 innerIterations=1, outerIterations=30, scaleStep=0.8, gamma=0.0, medianFiltering=1)
         if native is not None:
+            used = native.set_threads(native.usable_cpus())
+
             def one():
                 native.calc(I0, I1, P)
-            kind, sample, scale = "port", "full 1920x1080 pair per step, C/OpenMP port of optflow/src/tvl1flow.cpp, %d threads" % cores, 1.0
-            used = cores
+            kind, sample, scale = "port", ("full 1920x1080 pair per step, C/OpenMP port of optflow/src/tvl1flow.cpp, "
+                                           "%d threads (host reports %d logical CPUs)" % (used, cores)), 1.0
         else:
             # numpy restatement: bounded to a 480x270 crop (1/16 of the pixels), throughput scaled by area
             c0, c1 = I0[:270, :480].copy(), I1[:270, :480].copy()
@@ -308,6 +320,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     for _ in range(args.steps):
         step()
     e1.record()
+    if rank == 0:
+        sampler.sample_now()  # the steps above are asynchronous: the GPU is still working through them
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:

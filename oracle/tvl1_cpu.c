@@ -20,6 +20,9 @@
  */
 #include <float.h>
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdlib.h>
 #include <string.h>
 
@@ -260,6 +263,17 @@ void tvl1_cpu_remap_cubic(const float *src, int h, int w, const float *mapx, con
 /* OpticalFlowDual_TVL1::calc (tvl1flow.cpp:402-533), gamma = 0, medianFiltering = 1.
  * I0/I1: float32 already scaled to 0..255 (the caller applies the x1 / x255 rule of :429-430).
  * flow: interleaved (u, v) float32.  Returns 0 on success. */
+/* thread count for every parallel region (bench.py passes the CPUs this process may actually use) */
+int tvl1_cpu_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 int tvl1_cpu_calc(const tvl1_cpu_params *P, const float *I0, const float *I1, int rows, int cols, float *flow) {
     if (!P || P->nscales <= 0 || P->gamma != 0.0 || P->medianFiltering > 1 || P->useInitialFlow) return -1;
     int nscales = P->nscales;

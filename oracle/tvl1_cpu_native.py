@@ -24,10 +24,44 @@ def available() -> bool:
     return os.path.exists(_PATH)
 
 
+def usable_cpus() -> int:
+    """CPUs this process may really use: affinity mask capped by the cgroup CPU quota (a container on a
+    128-thread host is often limited to a few cores; 128 spinning OpenMP threads on 16 cores run ~35x slower)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
+def set_threads(n: int) -> int:
+    l = lib()
+    return int(l.tvl1_cpu_set_threads(int(n)))
+
+
 def lib():
     global _lib
     if _lib is None:
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         _lib = C.CDLL(_PATH)
+        _lib.tvl1_cpu_set_threads.restype = C.c_int
+        _lib.tvl1_cpu_set_threads.argtypes = [C.c_int]
+        _lib.tvl1_cpu_set_threads(usable_cpus())
         fp = C.POINTER(C.c_float)
         _lib.tvl1_cpu_calc.restype = C.c_int
         _lib.tvl1_cpu_calc.argtypes = [C.POINTER(_Params), fp, fp, C.c_int, C.c_int, fp]
