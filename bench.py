@@ -27,7 +27,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # keep stdout to the one JSON line (some boxes export NCCL_DEBUG=VERSION, which prints to stdout)
-os.environ["NCCL_DEBUG"] = os.environ.get("B2F_NCCL_DEBUG", "WARN")
+if os.environ.get("B2F_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = os.environ["B2F_NCCL_DEBUG"]
+else:  # NCCL prints its version banner to stdout at both VERSION and WARN level
+    os.environ.pop("NCCL_DEBUG", None)
 
 H, W = 1080, 1920
 WORKLOADS = {

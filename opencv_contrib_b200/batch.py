@@ -66,6 +66,8 @@ class FlowBatcher:
 
         def work(k: int):
             try:
+                # the CUDA current device is per thread: a fresh thread starts on device 0
+                self.torch.cuda.set_device(self.device)
                 for i in range(k, len(pairs), self.n_streams):
                     a, b = pairs[i]
                     self.algs[k].calc_host(a, b, flows[i], self.streams[k])

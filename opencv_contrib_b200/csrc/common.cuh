@@ -96,6 +96,47 @@ struct Ctx {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Device scope: the CUDA current device is per host thread.  A caller that drives several GPUs (or one GPU
+// from worker threads that never called cudaSetDevice) passes a stream / device pointers of device N while
+// the thread's current device is still 0; every entry point therefore switches to the device that owns the
+// stream (or, for the NULL stream, the input image) for the duration of the call and restores it afterwards.
+// The reference leaves this to the caller (cv::cuda::setDevice per thread).
+// ---------------------------------------------------------------------------------------------
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    DeviceScope(const void *device_ptr, cudaStream_t s) {
+        int target = -1;
+        if (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+            if (cudaStreamGetDevice(s, &target) != cudaSuccess) {
+                cudaGetLastError();
+                target = -1;
+            }
+        }
+        if (target < 0 && device_ptr) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, device_ptr) == cudaSuccess &&
+                (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged))
+                target = a.device;
+            else
+                cudaGetLastError();
+        }
+        enter(target);
+    }
+    explicit DeviceScope(int target) { enter(target); }
+    ~DeviceScope() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceScope(const DeviceScope &) = delete;
+    DeviceScope &operator=(const DeviceScope &) = delete;
+
+private:
+    void enter(int target) {
+        if (target >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != target) switched = cudaSetDevice(target) == cudaSuccess;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Handle base
 // ---------------------------------------------------------------------------------------------
 enum Algo { ALGO_TVL1 = 1, ALGO_FARNEBACK = 2, ALGO_BROX = 3, ALGO_DENSELK = 4 };

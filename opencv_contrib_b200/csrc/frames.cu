@@ -162,6 +162,7 @@ extern "C" int b2f_interpolate_frames(const b2f_image *frame0, const b2f_image *
     if (flags != B2F_INTERP_REFERENCE && flags != B2F_INTERP_CORRECTED) return B2F_BAD_ARG;
 
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    DeviceScope dev(frame0->data, s);
     FramePlanes P;
     P.w = frame0->cols;
     P.h = frame0->rows;

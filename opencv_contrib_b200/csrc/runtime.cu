@@ -165,6 +165,7 @@ int b2f_calc(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_image 
     int st = check_images(I0, I1, flow);
     if (st != B2F_OK) return st;
     h->stats.calls++;
+    b2f::DeviceScope dev(I0->data, static_cast<cudaStream_t>(cuda_stream));
     return h->calc(I0, I1, flow, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -177,6 +178,7 @@ int b2f_calc_uv(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_ima
     if (u->type != B2F_32FC1 || v->type != B2F_32FC1) return B2F_UNSUPPORTED_TYPE;
     if (v->rows != u->rows || v->cols != u->cols) return B2F_SIZE_MISMATCH;
     h->stats.calls++;
+    b2f::DeviceScope dev(I0->data, static_cast<cudaStream_t>(cuda_stream));
     h->planar_v = v->data;
     h->planar_v_step = v->step;
     st = h->calc(I0, I1, u, static_cast<cudaStream_t>(cuda_stream));
@@ -204,6 +206,7 @@ int b2f_calc_host(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_i
     if (I1->rows != I0->rows || I1->cols != I0->cols || flow->rows != I0->rows || flow->cols != I0->cols)
         return B2F_SIZE_MISMATCH;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    b2f::DeviceScope dev(nullptr, s);  // host buffers: the stream names the device
     const int rows = I0->rows, cols = I0->cols;
     size_t in_pitch = (cols * es + 255) & ~size_t(255);
     size_t fl_pitch = (cols * fs + 255) & ~size_t(255);

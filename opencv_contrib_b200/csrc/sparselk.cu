@@ -240,6 +240,7 @@ int b2f_sparselk_calc(b2f_sparse *h, const b2f_image *prev_img, const b2f_image 
     if (prev_img->step < prev_img->cols * es || next_img->step < next_img->cols * es) return B2F_BAD_ARG;
     const int rows = prev_img->rows, cols = prev_img->cols;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    DeviceScope dev(prev_img->data, s);
 
     Ctx c;
     c.stream = s;

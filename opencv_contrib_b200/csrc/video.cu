@@ -31,6 +31,7 @@ struct b2f_video {
     std::vector<cudaEvent_t> copy_done, comp_done, down_done;
     std::vector<int64_t> flow_pair;  // which pair each flow slot currently holds (-1 = none)
     int last_error = 0;
+    int device = 0;            // the front end lives on the device that was current at creation
 
     char *d_frame(int64_t k) const { return d_frames + (size_t)(k % nf) * in_pitch * rows; }
     char *h_frame(int64_t k) const { return h_frames + (size_t)(k % nf) * esz * cols * rows; }
@@ -58,6 +59,7 @@ extern "C" {
 
 void b2f_video_destroy(b2f_video *v) {
     if (!v) return;
+    b2f::DeviceScope dev(v->device);
     if (v->s_copy) cudaStreamSynchronize(v->s_copy);
     if (v->s_comp) cudaStreamSynchronize(v->s_comp);
     if (v->s_down) cudaStreamSynchronize(v->s_down);
@@ -81,6 +83,7 @@ int b2f_video_create(b2f_handle *h, int rows, int cols, int type, int depth, int
     *out = nullptr;
     b2f_video *v = new b2f_video;
     v->h = h;
+    cudaGetDevice(&v->device);
     v->rows = rows;
     v->cols = cols;
     v->type = type;
@@ -137,6 +140,7 @@ int b2f_video_create(b2f_handle *h, int rows, int cols, int type, int depth, int
 int b2f_video_push(b2f_video *v, const void *host_frame, size_t step, int64_t *pair_index) {
     if (!v || !host_frame) return B2F_BAD_ARG;
     if (step < v->esz * (size_t)v->cols) return B2F_BAD_ARG;
+    b2f::DeviceScope dev(v->device);
     const int64_t k = v->pushed;
     const int64_t p = k - 1;  // pair this frame completes
     if (pair_index) *pair_index = p;
@@ -190,6 +194,7 @@ int b2f_video_push(b2f_video *v, const void *host_frame, size_t step, int64_t *p
 int b2f_video_fetch(b2f_video *v, int64_t pair_index, void *host_flow, size_t step) {
     if (!v || !host_flow || pair_index < 0) return B2F_BAD_ARG;
     if (step < 8 * (size_t)v->cols) return B2F_BAD_ARG;
+    b2f::DeviceScope dev(v->device);
     const int slot = static_cast<int>(pair_index % v->depth);
     if (v->flow_pair[slot] != pair_index) return B2F_BAD_ARG;  // not pushed yet, or already overwritten
     VCHECK(cudaEventSynchronize(v->down_done[slot]));
@@ -202,6 +207,7 @@ int b2f_video_fetch(b2f_video *v, int64_t pair_index, void *host_flow, size_t st
 
 int b2f_video_fetch_view(b2f_video *v, int64_t pair_index, const float **host_flow, size_t *step) {
     if (!v || !host_flow || !step || pair_index < 0) return B2F_BAD_ARG;
+    b2f::DeviceScope dev(v->device);
     const int slot = static_cast<int>(pair_index % v->depth);
     if (v->flow_pair[slot] != pair_index) return B2F_BAD_ARG;
     VCHECK(cudaEventSynchronize(v->down_done[slot]));

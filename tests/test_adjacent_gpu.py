@@ -164,3 +164,35 @@ def test_video_warm_start_chains_the_previous_flow(cuda_device, name):
     assert st["mean"] < 0.5, st
     with pytest.raises(ocb.B2FError):  # Brox has no initial-flow path
         ocb.VideoFlow(_algs(ocb)["brox"][0](), 120, 168, dtype=np.float32, warm_start=True)
+
+
+def test_entry_points_follow_the_stream_device_not_the_thread_device(cuda_device):
+    """The CUDA current device is per host thread; a worker thread that never called cudaSetDevice sits on
+    device 0.  Every entry point switches to the device that owns the stream / the images for the call."""
+    import threading
+    import torch
+    import opencv_contrib_b200 as ocb
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    d1 = torch.device("cuda:1")
+    I0, I1, _ = synth.make_pair(96, 128, seed=2, kind="const")
+    ref = ocb.FarnebackOpticalFlow_create(numLevels=3).calc_host(I0, I1)  # device 0, main thread
+    out = {}
+
+    def work():
+        try:
+            assert torch.cuda.current_device() == 0
+            s = torch.cuda.Stream(device=d1)
+            alg = ocb.FarnebackOpticalFlow_create(numLevels=3)
+            out["host"] = alg.calc_host(I0, I1, None, s)
+            a, b = torch.from_numpy(I0).to(d1), torch.from_numpy(I1).to(d1)
+            out["dev"] = alg.calc(a, b, torch.empty((96, 128, 2), device=d1), s).cpu().numpy()
+            assert torch.cuda.current_device() == 0  # restored
+        except BaseException as e:  # noqa: BLE001
+            out["err"] = e
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert "err" not in out, out.get("err")
+    assert np.array_equal(out["host"], ref) and np.array_equal(out["dev"], ref)
