@@ -186,7 +186,9 @@ def test_entry_points_follow_the_stream_device_not_the_thread_device(cuda_device
             alg = ocb.FarnebackOpticalFlow_create(numLevels=3)
             out["host"] = alg.calc_host(I0, I1, None, s)
             a, b = torch.from_numpy(I0).to(d1), torch.from_numpy(I1).to(d1)
-            out["dev"] = alg.calc(a, b, torch.empty((96, 128, 2), device=d1), s).cpu().numpy()
+            f = alg.calc(a, b, torch.empty((96, 128, 2), device=d1), s)
+            s.synchronize()  # calc is asynchronous on `s`
+            out["dev"] = f.cpu().numpy()
             assert torch.cuda.current_device() == 0  # restored
         except BaseException as e:  # noqa: BLE001
             out["err"] = e
