@@ -423,13 +423,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tvl1", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=32, help="frame pairs per step per GPU")
-    ap.add_argument("--streams", type=int, default=4, help="engine instances / CUDA streams per GPU")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="engine instances / CUDA streams per GPU (0 = per workload: 4 for tvl1, whose persistent kernels "
+                         "fill the GPU on their own; 8 for farneback, whose coarse levels are launch-bound)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary single-stream measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.streams <= 0:
+        args.streams = 8 if args.workload == "farneback" else 4
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
