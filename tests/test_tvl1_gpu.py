@@ -207,3 +207,23 @@ def test_1080p_round_trip_properties(cuda_device):
     assert float(np.abs(z).max()) <= 1e-3
     again, _ = _run(cuda_device, I0, I1, **kw)          # run-to-run determinism
     assert np.array_equal(again, got)
+
+
+def test_1080p_baseline_config_vs_cpu_oracle(cuda_device):
+    """BASELINE configs[2] at full size: 1920x1080, 5 scales / 10 warps / 30 iterations, eps = 0, against the CPU
+    oracle (the C/OpenMP port of modules/optflow/src/tvl1flow.cpp; a few seconds on the box's cores) at the
+    reference's own GPU-vs-CPU acceptance level (test_optflow.cpp:456-465: NCC similarity; plus the regression
+    criterion of test_tvl1optflow.cpp:114-142, >= 95 % of the pixels within 0.1 px)."""
+    from oracle import tvl1_cpu_native
+    if not tvl1_cpu_native.available():
+        pytest.skip("oracle/_build/libtvl1_cpu.so not built")
+    I0, I1, gt = synth.make_pair(1080, 1920, seed=0, kind="smooth")
+    got, _ = _run(cuda_device, I0, I1, nscales=5, warps=10, epsilon=0.0, iterations=30)
+    cpu = tvl1_cpu_native.calc(I0, I1, tvl1_cpu.TVL1Params(nscales=5, warps=10, epsilon=0.0, innerIterations=1,
+                                                           outerIterations=30, medianFiltering=1))
+    st = metrics.epe_stats(got, cpu, border=32)
+    ncc = metrics.ncc_dissimilarity(got[32:-32, 32:-32], cpu[32:-32, 32:-32])
+    assert st["frac_le_0.1"] >= 0.95 and st["mean"] <= 0.08 and ncc <= 4e-3, (st, ncc)
+    # and both recover the synthetic motion equally well
+    g_gpu, g_cpu = metrics.epe_stats(got, gt, border=32), metrics.epe_stats(cpu, gt, border=32)
+    assert abs(g_gpu["mean"] - g_cpu["mean"]) <= 0.05, (g_gpu, g_cpu)
