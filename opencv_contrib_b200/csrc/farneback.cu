@@ -528,8 +528,8 @@ __global__ void __launch_bounds__(256) k_farn_iter(Stack5 Min, Stack5 Mout, Stac
 // ------------------------------------------------------------------------------------------
 constexpr int FT_W = 64, FT_H = 32;
 
-template <int K, bool GAUSS, bool QUAD>
-__global__ void __launch_bounds__(256) k_farn_iter_fast(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
+template <int K, bool GAUSS, bool QUAD, int NT = 256>
+__global__ void __launch_bounds__(NT) k_farn_iter_fast(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
                                                         Plane flowy, int rows, int cols, float box_inv,
                                                         const float *__restrict__ g, int update_matrices,
                                                         int write_flow) {
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256) k_farn_iter_fast(Stack5 Min, Stack5 Mout,
 
     // ---- vertical pass ----
     const size_t plane_stride = (size_t)Min.h * Min.pitch;
-    for (int task = tid; task < SW * 5 * 2; task += 256) {
+    for (int task = tid; task < SW * 5 * 2; task += NT) {
         const int half = task / (SW * 5);
         const int rem = task - half * (SW * 5);
         const int pl = rem / SW, i = rem - pl * SW;
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(256) k_farn_iter_fast(Stack5 Min, Stack5 Mout,
 
     // ---- horizontal pass + 2x2 solve + matrix update, 4 pixels per task ----
 #pragma unroll 1
-    for (int task = tid; task < FT_H * (FT_W / 4); task += 256) {
+    for (int task = tid; task < FT_H * (FT_W / 4); task += NT) {
         const int r = task / (FT_W / 4), q = task - r * (FT_W / 4);
         const int y = y0 + r, x = x0 + 4 * q;
         if (y >= rows || x >= cols) continue;
@@ -668,6 +668,7 @@ class FarnebackEngine : public b2f_handle {
 public:
     explicit FarnebackEngine(const b2f_farneback_params &p) : P(p) { algo = ALGO_FARNEBACK; }
     b2f_farneback_params P;
+    int num_sms_ = 0;
 
     int calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, cudaStream_t s) override;
     int set_param(int id, double v) override;
@@ -820,12 +821,17 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
         static bool attr_done[64] = {};
         int dev = 0;
         cudaGetDevice(&dev);
+        if (!num_sms_) {
+            cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev);
+            if (num_sms_ <= 0) num_sms_ = 148;
+        }
         if (dev >= 0 && dev < 64 && !attr_done[dev]) {
             const int bytes = (int)(sizeof(float) * 5 * FT_H * (FT_W + 12));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             attr_done[dev] = c.ok();
         }
     }
@@ -911,6 +917,9 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
         const bool fast6 = khalf == 6 && knobs.kernel_path != 1;
         const dim3 gf(div_up(w, FT_W), div_up(h, FT_H));
         const size_t smem_fast = sizeof(float) * 5 * FT_H * (FT_W + 12);
+        // Coarse levels leave most SMs idle and are bound by each thread's chain of dependent round trips (three
+        // column tasks, two quad tasks): 512 threads per tile halve that chain.  Same arithmetic, same bits.
+        const bool wide_blocks = (int)(gf.x * gf.y) <= num_sms_ && knobs.fused_iters != 256;
         for (int i = 0; i < P.num_iters; ++i) {
             const int upd = i < P.num_iters - 1;  // farneback.cpp:468-470
             const int wflow = !upd;
@@ -923,6 +932,9 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
                 else if (gauss)
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, true, false>), gf, dim3(256), smem_fast, Ma, Mb, R0,
                                R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else if (quad && wide_blocks)
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 512>), gf, dim3(512), smem_fast, Ma, Mb,
+                               R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
                 else if (quad)
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true>), gf, dim3(256), smem_fast, Ma, Mb, R0,
                                R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
