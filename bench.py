@@ -44,6 +44,14 @@ WORKLOADS = {
 }
 
 
+BATCH_PARAMS = {
+    "tvl1": dict(tau=0.25, lambda_=0.15, theta=0.3, nscales=5, warps=10, epsilon=0.0, iterations=30, scale_step=0.8,
+                 gamma=0.0, use_initial_flow=0),
+    "farneback": dict(num_levels=5, pyr_scale=0.5, fast_pyramids=0, win_size=13, num_iters=10, poly_n=5, poly_sigma=1.1,
+                      flags=0),
+}
+
+
 def make_alg(workload: str):
     import opencv_contrib_b200 as ocb
     if workload == "tvl1":
@@ -286,7 +294,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from opencv_contrib_b200.batch import FlowBatcher, gather_flows
+    from opencv_contrib_b200.batch import NativeFlowBatch, gather_flows
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -299,7 +307,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     pairs = [(frames[i], frames[i + 1]) for i in range(B)]
     flows = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev)
     flow_views = [flows[i] for i in range(B)]
-    batcher = FlowBatcher(lambda: make_alg(args.workload), n_streams=args.streams, device=dev)
+    # native batch front end (csrc/batch.cu): N engine handles on N streams, one C call per batch
+    batcher = NativeFlowBatch(args.workload, BATCH_PARAMS[args.workload], n_streams=args.streams)
 
     def step():
         batcher.run_device(pairs, flow_views)

@@ -236,6 +236,27 @@ B2F_API int b2f_interpolate_frames(const b2f_image *frame0, const b2f_image *fra
                                    const b2f_image *fv, const b2f_image *bu, const b2f_image *bv, float pos,
                                    b2f_image *new_frame, b2f_image *buf, int flags, void *cuda_stream);
 
+/* ---- batched frame-pair front end for one GPU: N engine handles on N streams, pairs dealt
+ *      round robin -- the pattern of the reference's own multi-stream test (test/test_optflow.cpp:468-528).
+ *      algo: 1 TV-L1, 2 Farneback, 3 Brox, 4 DensePyrLK; params: the matching b2f_*_params (NULL = defaults).
+ *      Sharding over GPUs / processes and the NCCL result gather stay with the caller's process framework
+ *      (opencv_contrib_b200/batch.py over torch.distributed). ---- */
+typedef struct b2f_batch b2f_batch;
+B2F_API int b2f_batch_create(int algo, const void *params, int n_streams, b2f_batch **out);
+B2F_API int b2f_batch_streams(const b2f_batch *b);
+B2F_API b2f_handle *b2f_batch_engine(b2f_batch *b, int i); /* borrowed: engine i, e.g. for b2f_get_stats */
+B2F_API int b2f_batch_set_param(b2f_batch *b, int id, double value); /* every engine */
+/* n_pairs device-resident pairs -> flows.  Forked from / joined to `stream` with events only: no host
+ * synchronisation, CUDA events on `stream` bracket the whole batch. */
+B2F_API int b2f_batch_run_device(b2f_batch *b, int n_pairs, const b2f_image *I0, const b2f_image *I1,
+                                 b2f_image *flow, void *cuda_stream);
+/* n_pairs HOST pairs -> host flows: one worker thread per stream runs b2f_calc_host on its share, so the copies
+ * of one pair overlap the solves of the others.  Returns when every flow has landed. */
+B2F_API int b2f_batch_run_host(b2f_batch *b, int n_pairs, const b2f_image *I0, const b2f_image *I1, b2f_image *flow);
+B2F_API uint64_t b2f_batch_launches(b2f_batch *b);
+B2F_API int b2f_batch_reset_stats(b2f_batch *b);
+B2F_API void b2f_batch_destroy(b2f_batch *b);
+
 /* ---- video front end: consecutive frames of one stream -> flow(k-1 -> k).
  *      Each pushed HOST frame is uploaded once (the previous frame stays resident), the solve for
  *      pair k overlaps the upload of frame k+1 and the download of flow k-1 (three streams, events,

@@ -110,6 +110,15 @@ SYMBOLS = [
     ("b2f_sparselk_calc", C.c_int, [_H, _IMG, _IMG, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_void_p]),
     ("b2f_sparselk_destroy", None, [_H]),
+    ("b2f_batch_create", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(_H)]),
+    ("b2f_batch_streams", C.c_int, [_H]),
+    ("b2f_batch_engine", C.c_void_p, [_H, C.c_int]),
+    ("b2f_batch_set_param", C.c_int, [_H, C.c_int, C.c_double]),
+    ("b2f_batch_run_device", C.c_int, [_H, C.c_int, _IMG, _IMG, _IMG, C.c_void_p]),
+    ("b2f_batch_run_host", C.c_int, [_H, C.c_int, _IMG, _IMG, _IMG]),
+    ("b2f_batch_launches", C.c_uint64, [_H]),
+    ("b2f_batch_reset_stats", C.c_int, [_H]),
+    ("b2f_batch_destroy", None, [_H]),
     ("b2f_flo_read_size", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("b2f_flo_read", C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
     ("b2f_flo_write", C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),

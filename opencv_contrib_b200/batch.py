@@ -90,6 +90,78 @@ class FlowBatcher:
             a.resetStats()
 
 
+class NativeFlowBatch:
+    """Same interface as FlowBatcher, but the stream fork / join, the round-robin deal and the host-path worker
+    threads live in libb200flow.so (csrc/batch.cu, ``b2f_batch_*``): one C call per batch instead of one per pair.
+
+        NativeFlowBatch("tvl1", dict(nscales=5, warps=10, epsilon=0.0, iterations=30), n_streams=4)
+    """
+
+    _ALGO = {"tvl1": 1, "farneback": 2, "brox": 3, "denselk": 4}
+
+    def __init__(self, family: str, params: dict | None = None, n_streams: int = 4):
+        import ctypes as C
+        from . import _lib
+        self._C, self._libmod = C, _lib
+        self._lib = _lib.lib()
+        struct = {"tvl1": _lib.b2f_tvl1_params, "farneback": _lib.b2f_farneback_params, "brox": _lib.b2f_brox_params,
+                  "denselk": _lib.b2f_denselk_params}[family]()
+        getattr(self._lib, "b2f_%s_default_params" % family)(C.byref(struct))
+        for k, v in (params or {}).items():
+            if not hasattr(struct, k):
+                raise AttributeError("%s has no parameter %r" % (family, k))
+            setattr(struct, k, v)
+        self._b = C.c_void_p()
+        st = self._lib.b2f_batch_create(self._ALGO[family], C.byref(struct), n_streams, C.byref(self._b))
+        if st != 0:
+            self._b = None
+            raise _lib.B2FError(st)
+        self.n_streams = n_streams
+
+    def close(self):
+        b, self._b = getattr(self, "_b", None), None
+        if b:
+            self._lib.b2f_batch_destroy(b)
+
+    __del__ = close
+
+    def set_engine_option(self, name: str, value) -> None:
+        st = self._lib.b2f_batch_set_param(self._b, self._libmod.PARAM["engine"][name], float(value))
+        if st != 0:
+            raise self._libmod.B2FError(st)
+
+    def _arrays(self, pairs, flows, conv):
+        n = len(pairs)
+        arr = self._libmod.b2f_image * n
+        a, b, f = arr(), arr(), arr()
+        for i, ((x, y), fl) in enumerate(zip(pairs, flows)):
+            a[i], b[i], f[i] = conv(x), conv(y), conv(fl, True)
+        return n, a, b, f
+
+    def run_device(self, pairs, flows, stream=None) -> None:
+        import torch
+        from .cudaoptflow import _image_from_tensor
+        n, a, b, f = self._arrays(pairs, flows, _image_from_tensor)
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        st = self._lib.b2f_batch_run_device(self._b, n, a, b, f, self._C.c_void_p(stream.cuda_stream))
+        if st != 0:
+            raise self._libmod.B2FError(st)
+
+    def run_host(self, pairs, flows) -> None:
+        from .cudaoptflow import _image_from_numpy
+        n, a, b, f = self._arrays(pairs, flows, _image_from_numpy)
+        st = self._lib.b2f_batch_run_host(self._b, n, a, b, f)
+        if st != 0:
+            raise self._libmod.B2FError(st)
+
+    def launches(self) -> int:
+        return int(self._lib.b2f_batch_launches(self._b))
+
+    def reset_stats(self) -> None:
+        self._lib.b2f_batch_reset_stats(self._b)
+
+
 def gather_flows(local_flows, dst: int = 0, group=None):
     """Result gather to rank ``dst`` (NCCL on GPUs, gloo on CPU tensors).  ``local_flows`` is one
     stacked tensor (n_local, H, W, 2) with the same n_local on every rank.  Returns the list of

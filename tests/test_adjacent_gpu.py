@@ -198,3 +198,47 @@ def test_entry_points_follow_the_stream_device_not_the_thread_device(cuda_device
     t.join()
     assert "err" not in out, out.get("err")
     assert np.array_equal(out["host"], ref) and np.array_equal(out["dev"], ref)
+
+
+@pytest.mark.parametrize("family,params,dt", [
+    ("tvl1", dict(nscales=3, warps=2, epsilon=0.0, iterations=10), "u8"),
+    ("farneback", dict(num_levels=3, num_iters=3), "u8"),
+    ("brox", dict(inner_iterations=2, outer_iterations=10, solver_iterations=3), "f32")])
+def test_native_batch_front_end_equals_per_pair_calc(cuda_device, family, params, dt):
+    """b2f_batch_* (csrc/batch.cu): pairs dealt over engine handles on their own streams, forked from and joined
+    to the caller's stream -- same bits as one synchronous calc per pair, device and host paths."""
+    import torch
+    import opencv_contrib_b200 as ocb
+    from opencv_contrib_b200.batch import NativeFlowBatch
+    frames = _frames(8, 96, 136, dt)
+    pairs_h = [(frames[i], frames[i + 1]) for i in range(7)]
+    make = {"tvl1": lambda: ocb.OpticalFlowDual_TVL1_create(nscales=3, warps=2, epsilon=0.0, iterations=10),
+            "farneback": lambda: ocb.FarnebackOpticalFlow_create(numLevels=3, numIters=3),
+            "brox": lambda: ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, 2, 10, 3)}[family]
+    ref_alg = make()
+    want = [ref_alg.calc_host(a, b) for a, b in pairs_h]
+    nb = NativeFlowBatch(family, params, n_streams=3)
+    # device path on a side stream, bracketed by events on that stream
+    s = torch.cuda.Stream(device=cuda_device)
+    with torch.cuda.stream(s):
+        dev_pairs = [(torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device)) for a, b in pairs_h]
+        flows = torch.zeros((7, 96, 136, 2), device=cuda_device)
+        nb.run_device(dev_pairs, [flows[i] for i in range(7)], stream=s)
+        done = torch.cuda.Event()
+        done.record(s)
+    done.synchronize()  # the join made the caller's stream wait for every engine stream
+    got = flows.cpu().numpy()
+    for i in range(7):
+        assert np.array_equal(got[i], want[i]), i
+    assert nb.launches() > 0
+    # host path: worker threads inside the library
+    out = [np.zeros((96, 136, 2), np.float32) for _ in range(7)]
+    nb.run_host(pairs_h, out)
+    for i in range(7):
+        assert np.array_equal(out[i], want[i]), i
+    nb.reset_stats()
+    assert nb.launches() == 0
+    # argument errors propagate as status codes
+    with pytest.raises(ocb.B2FError):
+        nb.run_host([(frames[0], frames[1][:, :100])], [out[0]])
+    nb.close()
