@@ -213,6 +213,10 @@ void pyr_down(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, int drows
 // same for an 8-bit pyramid held in float planes: the result is rounded like saturate_cast<uchar> (pyr_down.cu:172)
 void pyr_down_u8(Ctx &c, int cls, Plane s, int srows, int scols, Plane d, int drows, int dcols);
 
+// 2-D float32 TMA descriptor (128-byte CUtensorMap written to map_out); false when the driver entry point is missing.
+bool tma_encode_2d_f32(void *map_out, const float *base, uint64_t width, uint64_t height, uint64_t pitch_bytes,
+                       uint32_t box_w, uint32_t box_h);
+
 // resize.cpp:76-84 scale rule: scale passed to the kernel is float(1/f).
 static inline float inv_scale_from_sizes(int src, int dst) { return static_cast<float>(1.0 / (static_cast<double>(dst) / src)); }
 

@@ -21,6 +21,8 @@
 // sparse blur, resize / pyrDown), 3 update_matrices0, 4 flow_init (prolong / split / merge).
 #include "common.cuh"
 
+#include <cuda.h>  // CUtensorMap (type only; encoded through tma_encode_2d_f32)
+
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -655,6 +657,195 @@ __global__ void __launch_bounds__(NT) k_farn_iter_fast(Stack5 Min, Stack5 Mout, 
 // ------------------------------------------------------------------------------------------
 // host engine
 // ------------------------------------------------------------------------------------------
+// Persistent TMA variant of the fast kernel for levels with many tiles (opt-in: kernel_path = 3).
+// One 512-thread CTA per SM walks 64x64 tiles.  The five M planes of a tile (+6 halo, rounded out to a 16-byte
+// aligned 80-column box) arrive through cp.async.bulk.tensor into shared memory, so the vertical pass reads
+// shared memory instead of issuing three dependent rounds of global loads per thread; as soon as the vertical
+// sums are formed the NEXT tile's boxes are requested into the same buffer and land while this tile runs its
+// horizontal pass, solve and R1 gather.  TMA zero-fills outside the tensor, the blur needs replicate borders:
+// border tiles patch their halo cells from the clamped in-tile position before the vertical pass.
+// Same arithmetic and summation order as k_farn_iter_fast -> bit-identical.
+// ------------------------------------------------------------------------------------------
+constexpr int TT = 64;              // tile edge
+constexpr int TB_W = TT + 16;       // box columns: x0-8 .. x0+71 (origin a multiple of 4 floats)
+constexpr int TB_H = TT + 12;       // box rows:    y0-6 .. y0+69
+constexpr int TSW = TT + 12;        // vertical-sum columns: x0-6 .. x0+69
+constexpr int TNT = 512;
+constexpr size_t FARN_TMA_SMEM = sizeof(float) * (5 * TB_H * TB_W + 5 * TT * TSW) + 64;
+
+__device__ __forceinline__ uint32_t farn_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void farn_mbar_wait(uint64_t *bar, uint32_t parity) {
+    // bounded: a descriptor / byte-count mistake must trap, not hang the GPU
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(farn_smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+template <bool GAUSS>
+__global__ void __launch_bounds__(TNT, 1)
+    k_farn_iter_tma(const __grid_constant__ CUtensorMap mapM, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx, Plane flowy,
+                    int rows, int cols, int plane_rows, float box_inv, const float *__restrict__ g, int update_matrices,
+                    int write_flow, int tiles_x, int ntiles) {
+    constexpr int K = 6;
+    extern __shared__ __align__(1024) float tsm[];
+    float *inbuf = tsm;                      // [5][TB_H][TB_W]
+    float *sums = tsm + 5 * TB_H * TB_W;     // [5][TT][TSW]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sums + 5 * TT * TSW);
+    const int tid = threadIdx.x;
+    constexpr uint32_t kBytes = 5 * TB_H * TB_W * sizeof(float);
+
+    float gk[K + 1];
+#pragma unroll
+    for (int j = 0; j <= K; ++j) gk[j] = GAUSS ? g[j] : 1.f;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(farn_smem_u32(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto request = [&](int t) {  // thread 0 only
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(farn_smem_u32(bar)), "r"(kBytes) : "memory");
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl)
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"(farn_smem_u32(inbuf + pl * TB_H * TB_W)), "l"(reinterpret_cast<uint64_t>(&mapM)), "r"(tx * TT - 8),
+                "r"(pl * plane_rows + ty * TT - K), "r"(farn_smem_u32(bar)) : "memory");
+    };
+
+    int t = blockIdx.x;
+    if (tid == 0 && t < ntiles) request(t);
+    uint32_t parity = 0;
+    for (; t < ntiles; t += gridDim.x) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int x0 = tx * TT, y0 = ty * TT;
+        farn_mbar_wait(bar, parity);
+        parity ^= 1;
+
+        // ---- replicate borders: patch cells whose coordinates clamp (zero-filled or foreign rows from TMA) ----
+        if (x0 - K < 0 || y0 - K < 0 || x0 + TT + K > cols || y0 + TT + K > rows) {
+            for (int e = tid; e < 5 * TB_H * TSW; e += TNT) {
+                const int pl = e / (TB_H * TSW);
+                const int rem = e - pl * (TB_H * TSW);
+                const int r = rem / TSW, i = rem - r * TSW;
+                const int y = y0 - K + r, x = x0 - K + i;
+                const int cy = clampi(y, 0, rows - 1), cx = clampi(x, 0, cols - 1);
+                if (cy != y || cx != x) {
+                    float *P = inbuf + pl * TB_H * TB_W;
+                    P[r * TB_W + i + 2] = P[(cy - (y0 - K)) * TB_W + (cx - (x0 - K)) + 2];
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- vertical pass from shared memory: task = (16-row strip, plane, column) ----
+        for (int task = tid; task < 4 * 5 * TSW; task += TNT) {
+            const int strip = task / (5 * TSW);
+            const int rem = task - strip * (5 * TSW);
+            const int pl = rem / TSW, i = rem - pl * TSW;
+            const float *col = inbuf + (pl * TB_H + strip * 16) * TB_W + i + 2;
+            float v[16 + 2 * K];
+#pragma unroll
+            for (int q = 0; q < 16 + 2 * K; ++q) v[q] = col[q * TB_W];
+            float *dst = sums + (pl * TT + strip * 16) * TSW + i;
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                float acc = GAUSS ? v[o + K] * gk[0] : v[o + K];
+#pragma unroll
+                for (int j = 1; j <= K; ++j) {
+                    const float s2 = v[o + K - j] + v[o + K + j];
+                    acc = GAUSS ? acc + s2 * gk[j] : acc + s2;
+                }
+                dst[o * TSW] = acc;
+            }
+        }
+        __syncthreads();  // sums complete, inbuf free
+
+        const int tn = t + gridDim.x;
+        if (tid == 0 && tn < ntiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            request(tn);
+        }
+
+        // ---- horizontal pass + 2x2 solve + matrix update, 4 pixels per task (as k_farn_iter_fast) ----
+#pragma unroll 1
+        for (int task = tid; task < TT * (TT / 4); task += TNT) {
+            const int r = task / (TT / 4), q = task - r * (TT / 4);
+            const int y = y0 + r, x = x0 + 4 * q;
+            if (y >= rows || x >= cols) continue;
+            float res[5][4];
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl) {
+                const float *row = sums + (pl * TT + r) * TSW + 4 * q;
+                float w[4 + 2 * K + 2];
+#pragma unroll
+                for (int c = 0; c < (4 + 2 * K + 3) / 4; ++c) {
+                    const float4 tq = *reinterpret_cast<const float4 *>(row + 4 * c);
+                    w[4 * c] = tq.x;
+                    w[4 * c + 1] = tq.y;
+                    if (4 * c + 2 < 4 + 2 * K + 2) w[4 * c + 2] = tq.z;
+                    if (4 * c + 3 < 4 + 2 * K + 2) w[4 * c + 3] = tq.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float acc = GAUSS ? w[e + K] * gk[0] : w[e + K];
+#pragma unroll
+                    for (int i = 1; i <= K; ++i) {
+                        const float s2 = w[e + K - i] + w[e + K + i];
+                        acc = GAUSS ? acc + s2 * gk[i] : acc + s2;
+                    }
+                    res[pl][e] = GAUSS ? acc : acc * box_inv;
+                }
+            }
+            float fx[4], fy[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float g11 = res[0][e], g12 = res[1][e], g22 = res[2][e], h1 = res[3][e], h2 = res[4][e];
+                const float detInv = 1.f / (g11 * g22 - g12 * g12 + 1e-3f);
+                fx[e] = (g11 * h2 - g12 * h1) * detInv;
+                fy[e] = (g22 * h1 - g12 * h2) * detInv;
+            }
+            const bool full = x + 3 < cols;
+            if (write_flow) {
+                if (full) {
+                    *reinterpret_cast<float4 *>(&flowx.at(y, x)) = make_float4(fx[0], fx[1], fx[2], fx[3]);
+                    *reinterpret_cast<float4 *>(&flowy.at(y, x)) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+                } else {
+                    for (int e = 0; e < 4 && x + e < cols; ++e) {
+                        flowx.at(y, x + e) = fx[e];
+                        flowy.at(y, x + e) = fy[e];
+                    }
+                }
+            }
+            if (update_matrices) {
+                float m[4][5];
+                farn_update_matrices_quad(R0, R1, rows, cols, x, y, fx, fy, m);
+#pragma unroll
+                for (int pl = 0; pl < 5; ++pl) {
+                    if (full) {
+                        *reinterpret_cast<float4 *>(&Mout.at(pl, y, x)) = make_float4(m[0][pl], m[1][pl], m[2][pl], m[3][pl]);
+                    } else {
+                        for (int e = 0; e < 4 && x + e < cols; ++e) Mout.at(pl, y, x + e) = m[e][pl];
+                    }
+                }
+            }
+        }
+        __syncthreads();  // every warp is done with `sums` before the next tile's vertical pass overwrites it
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 struct FLevel {
     int rows = 0, cols = 0;
     double scale = 1.0;
@@ -832,6 +1023,8 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FARN_TMA_SMEM));
+            c.check(cudaFuncSetAttribute(k_farn_iter_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FARN_TMA_SMEM));
             attr_done[dev] = c.ok();
         }
     }
@@ -920,11 +1113,31 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
         // Coarse levels leave most SMs idle and are bound by each thread's chain of dependent round trips (three
         // column tasks, two quad tasks): 512 threads per tile halve that chain.  Same arithmetic, same bits.
         const bool wide_blocks = (int)(gf.x * gf.y) <= num_sms_ && knobs.fused_iters != 256;
+        // opt-in persistent TMA kernel (kernel_path 3) on levels with at least two waves of 64x64 tiles
+        const int tma_tx = div_up(w, TT), tma_ty = div_up(h, TT);
+        bool use_tma = knobs.kernel_path == 3 && khalf == 6 && tma_tx * tma_ty >= 2 * num_sms_;
+        alignas(64) CUtensorMap mapA, mapB;
+        if (use_tma) {
+            const uint64_t pitch_b = sizeof(float) * (uint64_t)plane_pitch(w);
+            use_tma = tma_encode_2d_f32(&mapA, Ma.p, (uint64_t)w, 5ull * h, pitch_b, TB_W, TB_H) &&
+                      tma_encode_2d_f32(&mapB, Mb.p, (uint64_t)w, 5ull * h, pitch_b, TB_W, TB_H);
+        }
+        bool a_is_input = true;
         for (int i = 0; i < P.num_iters; ++i) {
             const int upd = i < P.num_iters - 1;  // farneback.cpp:468-470
             const int wflow = !upd;
             const double bytes = npx * (20.0 + (upd ? 60.0 : 0.0) + (wflow ? 8.0 : 0.0));
-            if (fast6) {
+            if (use_tma) {
+                const int ntiles = tma_tx * tma_ty;
+                const dim3 gt(ntiles < num_sms_ ? ntiles : num_sms_);
+                const CUtensorMap &mapIn = a_is_input ? mapA : mapB;
+                if (gauss)
+                    B2F_LAUNCH(c, CLS_ITER, bytes, k_farn_iter_tma<true>, gt, dim3(TNT), FARN_TMA_SMEM, mapIn, Mb, R0, R1,
+                               lv.fx, lv.fy, h, w, h, box_inv, win_taps, upd, wflow, tma_tx, ntiles);
+                else
+                    B2F_LAUNCH(c, CLS_ITER, bytes, k_farn_iter_tma<false>, gt, dim3(TNT), FARN_TMA_SMEM, mapIn, Mb, R0, R1,
+                               lv.fx, lv.fy, h, w, h, box_inv, win_taps, upd, wflow, tma_tx, ntiles);
+            } else if (fast6) {
                 const bool quad = knobs.kernel_path != 2;
                 if (gauss && quad)
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, true, true>), gf, dim3(256), smem_fast, Ma, Mb, R0,
@@ -950,6 +1163,7 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
             Stack5 t = Ma;
             Ma = Mb;
             Mb = t;
+            a_is_input = !a_is_input;
             stats.iterations_run++;
         }
     }

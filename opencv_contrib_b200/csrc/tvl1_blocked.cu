@@ -402,6 +402,21 @@ static bool encode_plane(CUtensorMap *m, const Plane &P, int rows, int cols, int
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Generic 2-D float32 tiled tensor map (used by the Farneback persistent kernel as well): width x height elements,
+// row pitch in bytes, box_w x box_h element boxes, out-of-bounds elements read as zero.
+bool tma_encode_2d_f32(void *map_out, const float *base, uint64_t width, uint64_t height, uint64_t pitch_bytes,
+                       uint32_t box_w, uint32_t box_h) {
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[2] = {width, height};
+    const cuuint64_t gstr[1] = {pitch_bytes};
+    const cuuint32_t box[2] = {box_w, box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(static_cast<CUtensorMap *>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim,
+               gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // one block = two descriptor sets: [0] 72-wide boxes (any even origin), [1] 64-wide boxes (origin % 4 == 0)
 size_t tvl1_tma_maps_bytes() { return 2 * sizeof(TmaMaps); }
 

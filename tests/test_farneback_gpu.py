@@ -132,3 +132,20 @@ def test_1080p_vs_live_cpu_reference(cuda_device):
     assert metrics.epe_stats(got, cpu)["mean"] <= 0.02
     again, _ = _run(cuda_device, I0, I1)
     assert np.array_equal(again, got)
+
+
+@pytest.mark.parametrize("flags", [0, 256])
+def test_persistent_tma_iteration_kernel_bit_identical(cuda_device, flags):
+    """kernel_path = 3: levels with at least two waves of 64x64 tiles run the persistent kernel whose M tiles arrive
+    by TMA (zero fill patched to replicate borders).  Same arithmetic -> same bits, including ragged borders."""
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(1030, 1290, seed=3, kind="smooth")
+    d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
+    outs = []
+    for path in (0, 3):
+        alg = ocb.FarnebackOpticalFlow_create(numLevels=2, numIters=3, flags=flags)
+        alg.setEngineOption("kernel_path", path)
+        outs.append(alg.calc(d0, d1).cpu().numpy())
+    assert np.isfinite(outs[1]).all()
+    assert np.array_equal(outs[0], outs[1]), float(np.abs(outs[0] - outs[1]).max())
