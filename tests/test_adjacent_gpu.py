@@ -70,7 +70,8 @@ def test_interpolate_frames_matches_model(cuda_device, corrected, h, w, pitch):
         # accumulators, which the division by a small coverage amplifies (twice for the reference's bwdU):
         # compare strictly where the coverage is well away from zero
         c0, c1 = wbuf[0, :, :w], wbuf[1, :, :w]
-        assert np.abs(gb[0] - c0).max() < 5e-5 and np.abs(gb[1] - c1).max() < 5e-5
+        # relative to the coverage itself: where many sources converge the sums are large
+        assert (np.abs(gb[0] - c0) <= 5e-5 * np.maximum(1, c0)).all() and (np.abs(gb[1] - c1) <= 5e-5 * np.maximum(1, c1)).all()
         well = (c0 > 0.05) & (c1 > 0.05)
         assert well.mean() > 0.9
         for k in range(2, 6):
