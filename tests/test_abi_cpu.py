@@ -79,3 +79,19 @@ def test_null_and_bad_arguments_fail_loudly(lib):
     assert b"B2F_BAD_ARG" in lib.b2f_status_string(1)
     lib.b2f_destroy(h)
     assert lib.b2f_tvl1_create(None, None) == 1
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/b200flow.h is the drop-in boundary: it must compile as C (no C++ types, no torch types)."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "b200flow.h"\n'
+                   "int main(void) { b2f_error_stats s; b2f_sparselk_params p; b2f_image im; (void)s; (void)p; (void)im;\n"
+                   "  return B2F_OK; }\n")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
