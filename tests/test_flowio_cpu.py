@@ -153,3 +153,41 @@ def test_interpolate_model_reference_defects_are_visible():
     cleared_rows = (20 * 12) // 24                               # MemsetKernel clears the first w*h floats
     assert np.allclose(ref[0, cleared_rows + 1:, :20][fix[0, cleared_rows + 1:, :20] > 0]
                        / fix[0, cleared_rows + 1:, :20][fix[0, cleared_rows + 1:, :20] > 0], 2, atol=1e-5)
+
+
+# --------------------------------------------------------------------------- property tests (hypothesis)
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(h=st.integers(1, 40), w=st.integers(1, 40), pad=st.integers(0, 7), seed=st.integers(0, 2 ** 16))
+def test_flo_roundtrip_any_shape_and_pitch(tmp_path_factory, h, w, pad, seed):
+    rng = np.random.default_rng(seed)
+    big = rng.normal(0, 5, (h, w + pad, 2)).astype(np.float32)
+    f = big[:, pad // 2:pad // 2 + w]                    # row pitch != width * 8 when pad > 0
+    p = str(tmp_path_factory.mktemp("flo") / "x.flo")
+    flowio.writeOpticalFlow(p, f)
+    g = flowio.readOpticalFlow(p)
+    assert g.shape == (h, w, 2) and np.array_equal(g, f)
+    assert np.array_equal(cv2.readOpticalFlow(p), f)    # byte-compatible with the live reference reader
+
+
+@settings(max_examples=25, deadline=None)
+@given(h=st.integers(2, 30), w=st.integers(2, 30), seed=st.integers(0, 2 ** 16), shift=st.floats(-3, 3))
+def test_error_measures_invariants(h, w, seed, shift):
+    rng = np.random.default_rng(seed)
+    a = rng.normal(0, 2, (h, w, 2)).astype(np.float32)
+    b = (a + np.float32(shift)).astype(np.float32)
+    e = flowio.errorMap(a, b)
+    assert e.shape == (h, w) and (e >= 0).all()
+    assert np.allclose(e, np.abs(np.float32(shift)) * np.sqrt(2), atol=1e-5)
+    assert np.array_equal(flowio.errorMap(b, a), e)                      # symmetric
+    assert (flowio.errorMap(a, a) == 0).all()                            # identity
+    s = flowio.errorStats(e)
+    assert s["count"] == h * w and abs(s["mean"] - float(e.astype(np.float64).mean())) < 1e-9
+    assert all(0.0 <= r <= 1.0 for r in s["R"].values())
+    assert s["R"][0.5] >= s["R"][1.0] >= s["R"][2.0] >= s["R"][5.0] >= s["R"][10.0]   # monotone in the threshold
+    assert s["A"][0.5] <= s["A"][0.75] + 1e-9 <= s["A"][0.95] + 2e-9                  # monotone in the quantile
+    assert flowio.accuracy(a, a, 0.1) == 1.0
+    ang = flowio.errorMap(a, a, flowio.ERR_ANGULAR)
+    assert np.nanmax(np.abs(ang)) < 1e-3                                 # acos(1) up to float rounding
