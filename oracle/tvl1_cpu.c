@@ -11,9 +11,11 @@
  *   cv::resize(INTER_LINEAR, float)  centre-aligned bilinear, float weights (imgproc resize.cpp)
  *   cv::remap(INTER_CUBIC, float)    a = -0.75 bicubic, coordinates quantised to 1/32 px,
  *                                    BORDER_CONSTANT 0 (imgproc imgwarp.cpp, INTER_TAB_SIZE = 32)
- * cv::medianBlur is NOT restated: this port implements medianFiltering == 1 (off), the setting the
- * reference's own GPU-vs-CPU test uses (modules/cudaoptflow/test/test_optflow.cpp:456-460); the
- * numpy oracle (tvl1_cpu.py) covers the median path through cv2.medianBlur.
+ *   cv::medianBlur(float, 3|5)       exact median of the k x k window, BORDER_REPLICATE (imgproc
+ *                                    median_blur.simd.hpp, medianBlur_SortNet)
+ * tvl1_cpu_calc itself implements medianFiltering == 1 (off), the setting the reference's own
+ * GPU-vs-CPU test uses (modules/cudaoptflow/test/test_optflow.cpp:456-460); tvl1_cpu_median_blur
+ * serves oracle/_ref (the reference's own source compiled against ref_shim/), which calls it.
  * Parallelism mirrors the reference: cv::parallel_for_ over rows in every stage
  * (tvl1flow.cpp:682,735,821,887,968,1068,1220) -> `omp parallel for` over rows; estimateU's error
  * accumulation is serial in the reference (:1087-1113) and is a per-row reduction here.
@@ -252,7 +254,38 @@ static void proc_one_scale(const tvl1_cpu_params *P, const float *I0, const floa
     }
 }
 
+/* ---- cv::medianBlur, CV_32FC1, ksize 3 or 5 -------------------------------------------------- */
+/* OpenCV's float path is a sorting network over the k*k window with replicated borders, i.e. the exact
+ * median; src must not alias dst (the glue passes copies). */
+void tvl1_cpu_median_blur(const float *src, int h, int w, float *dst, int ksize) {
+    const int r = ksize / 2;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++) {
+        float win[25];
+        for (int x = 0; x < w; x++) {
+            int n = 0;
+            for (int dy = -r; dy <= r; dy++) {
+                int yy = y + dy; yy = yy < 0 ? 0 : (yy > h - 1 ? h - 1 : yy);
+                for (int dx = -r; dx <= r; dx++) {
+                    int xx = x + dx; xx = xx < 0 ? 0 : (xx > w - 1 ? w - 1 : xx);
+                    win[n++] = src[(size_t)yy * w + xx];
+                }
+            }
+            for (int i = 1; i < n; i++) { /* insertion sort: n <= 25 */
+                const float v = win[i];
+                int j = i - 1;
+                while (j >= 0 && win[j] > v) { win[j + 1] = win[j]; j--; }
+                win[j + 1] = v;
+            }
+            dst[(size_t)y * w + x] = win[n / 2];
+        }
+    }
+}
+
 /* debug / pinning entry points */
+void tvl1_cpu_resize_linear_f(const float *src, int sh, int sw, float *dst, int dh, int dw, double f) {
+    resize_linear(src, sh, sw, dst, dh, dw, f);
+}
 void tvl1_cpu_resize_linear(const float *src, int sh, int sw, float *dst, int dh, int dw) {
     resize_linear(src, sh, sw, dst, dh, dw, 0.0);
 }

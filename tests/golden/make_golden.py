@@ -1,6 +1,12 @@
-"""Generates the committed golden fixtures from the live CPU reference in the BUILD container
-(cv2 4.13.0: cv2.calcOpticalFlowFarneback = opencv/opencv modules/video/src/optflowgf.cpp, the
-function modules/optflow/src/interfaces.cpp:154-157 forwards to).   python tests/golden/make_golden.py"""
+"""Generates the committed golden fixtures in the BUILD container (the only place /root/reference exists):
+  farneback_*.npz  live CPU reference cv2.calcOpticalFlowFarneback (cv2 4.13.0 = opencv/opencv
+                   modules/video/src/optflowgf.cpp, the function modules/optflow/src/interfaces.cpp:154-157 forwards to)
+  tvl1_ref_*.npz   the reference's OWN CPU Dual TV-L1, /root/reference/modules/optflow/src/tvl1flow.cpp compiled
+                   unmodified into oracle/_ref/libtvl1_ref.so (oracle/Makefile, oracle/ref_shim/)
+  brox_720p.npz, denselk_1080p.npz   BASELINE-size outputs of the numpy restatements oracle/brox_model.py and
+                   oracle/denselk_model.py (no CPU implementation exists upstream: "parity unpinned"), stored as float16
+                   on a stride-4 grid plus full-resolution summary statistics -- minutes of numpy per case
+python tests/golden/make_golden.py [farneback] [tvl1] [brox] [denselk]      (no argument = farneback + tvl1)"""
 import os
 import sys
 
@@ -17,7 +23,8 @@ CASES = {
     "gauss": (dict(flags=256), 2e-2, 0.2),
     "scale08": (dict(pyrScale=0.8, numLevels=3), 1e-4, 0.02),
 }
-for name, (kw, ncc_tol, epe_tol) in CASES.items():
+WHAT = set(sys.argv[1:]) or {"farneback", "tvl1"}
+for name, (kw, ncc_tol, epe_tol) in (CASES.items() if "farneback" in WHAT else ()):
     I0, I1, _ = synth.make_pair(144, 192, seed=11, kind="smooth")
     flow = cv2.calcOpticalFlowFarneback(I0, I1, None, kw.get("pyrScale", 0.5), kw.get("numLevels", 5), 13, 10,
                                         kw.get("polyN", 5), kw.get("polySigma", 1.1), kw.get("flags", 0))
@@ -26,3 +33,20 @@ for name, (kw, ncc_tol, epe_tol) in CASES.items():
     out.update({"kw_" + k: v for k, v in kw.items()})
     np.savez_compressed(os.path.join(HERE, f"farneback_{name}.npz"), **out)
     print(name, flow.shape)
+
+if "tvl1" in WHAT:
+    from oracle import tvl1_cpu, tvl1_ref  # noqa: E402
+    TV = {
+        # the mapping the reference's GPU-vs-CPU test uses (cudaoptflow/test/test_optflow.cpp:456-460)
+        "gpu_twin": dict(nscales=4, warps=5, epsilon=0.0, innerIterations=1, outerIterations=30, medianFiltering=1),
+        "defaults": dict(),                                             # median 5, eps 0.01, 10 x 30
+        "gamma": dict(gamma=0.5, medianFiltering=1, epsilon=0.0, innerIterations=5, outerIterations=4),
+        "f32_median3": dict(medianFiltering=3, warps=2),
+    }
+    for name, kw in TV.items():
+        I0, I1, gt = synth.make_pair(120, 160, seed=21, kind="affine", dtype="f32" if name.startswith("f32") else "u8")
+        flow = tvl1_ref.calc(I0, I1, tvl1_cpu.TVL1Params(**kw))
+        out = {"I0": I0, "I1": I1, "flow": flow, "gt": gt.astype(np.float32), "source": tvl1_ref.source()}
+        out.update({"kw_" + k: v for k, v in kw.items()})
+        np.savez_compressed(os.path.join(HERE, f"tvl1_ref_{name}.npz"), **out)
+        print("tvl1", name, flow.shape, float(np.abs(flow).mean()))
