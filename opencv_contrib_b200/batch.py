@@ -162,17 +162,19 @@ class NativeFlowBatch:
         self._lib.b2f_batch_reset_stats(self._b)
 
 
-def gather_flows(local_flows, dst: int = 0, group=None):
+def gather_flows(local_flows, dst: int = 0, group=None, out=None):
     """Result gather to rank ``dst`` (NCCL on GPUs, gloo on CPU tensors).  ``local_flows`` is one
     stacked tensor (n_local, H, W, 2) with the same n_local on every rank.  Returns the list of
-    per-rank tensors on ``dst`` (index = rank, i.e. global pair order) and None elsewhere."""
+    per-rank tensors on ``dst`` (index = rank, i.e. global pair order) and None elsewhere.
+    ``out``: optional preallocated list of ``world`` receive tensors on ``dst`` (reused across steps)."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return [local_flows]
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    out = None
-    if rank == dst:
+    if rank != dst:
+        out = None
+    elif out is None:
         out = [local_flows.new_empty(local_flows.shape) for _ in range(world)]
     dist.gather(local_flows, out, dst=dst, group=group)
     return out

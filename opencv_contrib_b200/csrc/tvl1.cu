@@ -467,7 +467,9 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
         int done = 0;
         while (done < count) {
             const int kk = tvl1_blocked_pick_k(knobs.fused_iters, count - done, rows, cols);
-            if (use_tma)
+            if (use_tma && (knobs.kernel_path == 0 || knobs.kernel_path == 5))
+                tvl1_packed_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
+            else if (use_tma)  // kernel_path 4: the round-1 scalar TMA kernel (3: without elect.sync)
                 tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path != 3);
             else
                 tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);

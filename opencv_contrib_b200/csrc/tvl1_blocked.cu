@@ -367,6 +367,248 @@ __global__ void __launch_bounds__(NT, 1)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Packed-FP32 persistent TMA kernel (round 2; the default path).
+//
+// Same 64x64 region, same TMA staging, same arithmetic bit for bit -- but every thread now owns two
+// 4x1 pixel strips that are 32 rows apart: strip A in the upper half of the region (row tr) and strip B in
+// the lower half (row 32 + tr), and keeps each value as the pair (A, B) in one 64-bit register pair.
+// Because the two strips are translates of one another, EVERY neighbour relation holds pairwise (the left
+// neighbour of (A, B) is (A_left, B_left), the upper one (A_up, B_up)), so the whole update runs on
+// fma/add/mul.f32x2 with no repacking: 35 FP32 instructions per pixel-iteration become 17.5.
+// Vertical neighbours always belong to another thread row; they travel through four shared exchange arrays
+// whose slots hold ready-made (A, B) pairs:
+//   UP  (p12, p22): slot s = (row s-1, row 31+s), read by thread row s during the primal update
+//   DN  (u1,  u2 ): slot s = (row s+1, row 33+s), read by thread row s during the dual update
+// A thread row writes its natural pair to its neighbour's slot; only rows 31 / 32, where the halves meet,
+// are written as single elements (thread row 31 -> UP slot 0 .y, thread row 0 -> DN slot 31 .x).
+// Slot layout: [slot][half h = pixels 2h, 2h+1][lx] of float4 (A_2h, B_2h, A_2h+1, B_2h+1): consecutive lanes
+// read consecutive 16-byte words (conflict-free LDS.128 / STS.128).
+// Region origins are multiples of 4 (halo rounded up to a multiple of 4), so staging boxes are exactly the
+// region and the centre tile leaves as 16-byte vector stores.
+// ---------------------------------------------------------------------------------------------
+constexpr int PEX_F4 = 32 * 2 * 16;  // float4 per exchange array (32 slots x 2 halves x 16 lanes) = 16 KB
+
+struct RegsP {  // [i] = pixel column i of the thread's strips; .x = strip A (row tr), .y = strip B (row 32 + tr)
+    f2 Ix[4], Iy[4], ng[4], rc[4], u1[4], u2[4], p11[4], p12[4], p21[4], p22[4];
+};
+
+__device__ __forceinline__ void pex_publish(float4 *arr, int slot, int lx, const f2 (&v)[4]) {
+    arr[(slot * 2 + 0) * 16 + lx] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    arr[(slot * 2 + 1) * 16 + lx] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+}
+__device__ __forceinline__ void pex_fetch(const float4 *arr, int slot, int lx, f2 (&v)[4]) {
+    const float4 a = arr[(slot * 2 + 0) * 16 + lx], b = arr[(slot * 2 + 1) * 16 + lx];
+    v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+    v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+}
+// thread row 31: its strip A (row 31) is the upper neighbour of thread row 0's strip B (row 32)
+__device__ __forceinline__ void pex_publish_up_seam(float4 *arr, int lx, const f2 (&v)[4]) {
+    float *f0 = reinterpret_cast<float *>(&arr[(0 * 2 + 0) * 16 + lx]);
+    float *f1 = reinterpret_cast<float *>(&arr[(0 * 2 + 1) * 16 + lx]);
+    f0[1] = v[0].x; f0[3] = v[1].x; f1[1] = v[2].x; f1[3] = v[3].x;
+}
+// thread row 0: its strip B (row 32) is the lower neighbour of thread row 31's strip A (row 31)
+__device__ __forceinline__ void pex_publish_dn_seam(float4 *arr, int lx, const f2 (&v)[4]) {
+    float *f0 = reinterpret_cast<float *>(&arr[(31 * 2 + 0) * 16 + lx]);
+    float *f1 = reinterpret_cast<float *>(&arr[(31 * 2 + 1) * 16 + lx]);
+    f0[0] = v[0].y; f0[2] = v[1].y; f1[0] = v[2].y; f1[2] = v[3].y;
+}
+__device__ __forceinline__ f2 shfl_up2(f2 v) {
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1, 16), __shfl_up_sync(0xffffffffu, v.y, 1, 16));
+}
+__device__ __forceinline__ f2 shfl_down2(f2 v) {
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1, 16), __shfl_down_sync(0xffffffffu, v.y, 1, 16));
+}
+
+// gx: global x of the thread's first pixel; gyA: global y of strip A (strip B is 32 rows below).
+template <bool BORDER>
+__device__ __forceinline__ void tile_iterate_packed(RegsP &r, float4 *ex, int iters, const Tvl1Scalars k, int lx,
+                                                    int tr, int gx, int gyA, int W, int H) {
+    float4 *up12 = ex, *up22 = ex + PEX_F4, *dn1 = ex + 2 * PEX_F4, *dn2 = ex + 3 * PEX_F4;
+    const int gyB = gyA + 32;
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // thresholding constant, negated: rho * (-1/|grad|^2)
+        r.ng[i].x = -tvl1_inv_grad(r.ng[i].x);
+        r.ng[i].y = -tvl1_inv_grad(r.ng[i].y);
+    }
+
+    auto publish_up = [&]() {
+        if (tr < 31) { pex_publish(up12, tr + 1, lx, r.p12); pex_publish(up22, tr + 1, lx, r.p22); }
+        else { pex_publish_up_seam(up12, lx, r.p12); pex_publish_up_seam(up22, lx, r.p22); }
+    };
+    auto publish_dn = [&]() {
+        if (tr > 0) { pex_publish(dn1, tr - 1, lx, r.u1); pex_publish(dn2, tr - 1, lx, r.u2); }
+        else { pex_publish_dn_seam(dn1, lx, r.u1); pex_publish_dn_seam(dn2, lx, r.u2); }
+    };
+
+    publish_up();
+    __syncthreads();
+
+    for (int it = 0; it < iters; ++it) {
+        // ---------------- primal update (estimateU) ----------------
+        {
+            f2 u12[4], u22[4];
+            pex_fetch(up12, tr, lx, u12);
+            pex_fetch(up22, tr, lx, u22);
+            const f2 l11 = shfl_up2(r.p11[3]);
+            const f2 l21 = shfl_up2(r.p21[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                f2 pl11 = i ? r.p11[i ? i - 1 : 0] : l11;
+                f2 pl21 = i ? r.p21[i ? i - 1 : 0] : l21;
+                f2 pu12 = u12[i], pu22 = u22[i];
+                if (BORDER) {
+                    if (gx + i == 0) { pl11 = splat2(0.f); pl21 = splat2(0.f); }
+                    if (gyA == 0) { pu12.x = 0.f; pu22.x = 0.f; }
+                    if (gyB == 0) { pu12.y = 0.f; pu22.y = 0.f; }
+                }
+                f2 a, b;
+                tvl1_update_u_x2(k, r.Ix[i], r.Iy[i], r.ng[i], r.rc[i], r.u1[i], r.u2[i], r.p11[i], pl11, r.p12[i], pu12,
+                                 r.p21[i], pl21, r.p22[i], pu22, a, b);
+                r.u1[i] = a;
+                r.u2[i] = b;
+            }
+        }
+        publish_dn();
+        __syncthreads();
+
+        // ---------------- dual update (estimateDualVariables) ----------------
+        {
+            f2 d1[4], d2[4];
+            pex_fetch(dn1, tr, lx, d1);
+            pex_fetch(dn2, tr, lx, d2);
+            const f2 r1 = shfl_down2(r.u1[0]);
+            const f2 r2 = shfl_down2(r.u2[0]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const f2 c1 = r.u1[i], c2 = r.u2[i];
+                const f2 ur1 = i < 3 ? r.u1[i < 3 ? i + 1 : 3] : r1;
+                const f2 ur2 = i < 3 ? r.u2[i < 3 ? i + 1 : 3] : r2;
+                f2 ux1 = sub2(ur1, c1), uy1 = sub2(d1[i], c1);
+                f2 ux2 = sub2(ur2, c2), uy2 = sub2(d2[i], c2);
+                if (BORDER) {
+                    if (gx + i == W - 1) { ux1 = splat2(0.f); ux2 = splat2(0.f); }
+                    if (gyA == H - 1) { uy1.x = 0.f; uy2.x = 0.f; }
+                    if (gyB == H - 1) { uy1.y = 0.f; uy2.y = 0.f; }
+                }
+                tvl1_update_p2_x2(k.taut, ux1, uy1, ux2, uy2, r.p11[i], r.p12[i], r.p21[i], r.p22[i]);
+            }
+        }
+        publish_up();
+        __syncthreads();
+    }
+}
+
+// one strip (4 pixels of one row) of one plane -> global; full = all four columns inside the image
+__device__ __forceinline__ void store_strip(float *p, float v0, float v1, float v2, float v3, bool full, int ncols) {
+    if (full) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v0, v1, v2, v3);
+    } else {
+        if (ncols > 0) p[0] = v0;
+        if (ncols > 1) p[1] = v1;
+        if (ncols > 2) p[2] = v2;
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1)
+    k_tvl1_packed_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12,
+                      Plane o_p21, Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int tile,
+                      int tiles_x, int ntiles) {
+    extern __shared__ __align__(1024) float smem[];
+    float *stage = smem;
+    float4 *ex = reinterpret_cast<float4 *>(smem + N_IN * PLANE_F);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ex + 4 * PEX_F4);
+
+    const int tid = threadIdx.x;
+    const int lx = tid & 15, tr = tid >> 4;
+    constexpr uint32_t kStageBytes = N_IN * PLANE_F * sizeof(float);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // ghost halves of the seam slots (row -1 above the region, row 64 below it): never written afterwards
+    for (int i = tid; i < 4 * PEX_F4; i += NT) ex[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    int t = blockIdx.x;
+    const bool issuer = tid < 32 && elect_one();
+    if (issuer && t < ntiles) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        mbar_expect_tx(bar, kStageBytes);
+#pragma unroll
+        for (int pl = 0; pl < N_IN; ++pl)
+            tma_load_2d(stage + pl * PLANE_F, &maps.in[pl], tx * tile - halo, ty * tile - halo, bar);
+    }
+    uint32_t parity = 0;
+    for (; t < ntiles; t += gridDim.x) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int gx0 = tx * tile - halo, gy0 = ty * tile - halo;  // multiples of 4
+        mbar_wait(bar, parity);
+        parity ^= 1;
+
+        RegsP r;
+        {
+            const int oA = tr * R + 4 * lx, oB = oA + 32 * R;
+            auto ldpair = [&](int pl, f2 (&d)[4]) {
+                float a[4], b[4];
+                ld4(stage + pl * PLANE_F + oA, a);
+                ld4(stage + pl * PLANE_F + oB, b);
+                // x + (-0) == x bit for bit; the packed add makes ptxas materialise the (A, B) pair in an aligned
+                // register pair HERE, once per tile, instead of re-pairing the two LDS.128 results at every use
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] = add2(make_float2(a[i], b[i]), splat2(-0.0f));
+            };
+            ldpair(0, r.Ix);  ldpair(1, r.Iy);  ldpair(2, r.ng);  ldpair(3, r.rc);
+            ldpair(4, r.u1);  ldpair(5, r.u2);  ldpair(6, r.p11); ldpair(7, r.p12);
+            ldpair(8, r.p21); ldpair(9, r.p22);
+        }
+        __syncthreads();  // the staging buffer is free again
+
+        const int tn = t + gridDim.x;
+        if (issuer && tn < ntiles) {
+            const int ny = tn / tiles_x, nx = tn - ny * tiles_x;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, kStageBytes);
+#pragma unroll
+            for (int pl = 0; pl < N_IN; ++pl)
+                tma_load_2d(stage + pl * PLANE_F, &maps.in[pl], nx * tile - halo, ny * tile - halo, bar);
+        }
+
+        const int gxb = gx0 + 4 * lx, gyA = gy0 + tr;
+        const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
+        if (border)
+            tile_iterate_packed<true>(r, ex, iters, k, lx, tr, gxb, gyA, cols, rows);
+        else
+            tile_iterate_packed<false>(r, ex, iters, k, lx, tr, gxb, gyA, cols, rows);
+
+        // centre tile -> global: 16-byte stores (gxb and the valid column range are multiples of 4)
+        const int rx = 4 * lx;
+        if (rx >= halo && rx < R - halo && gxb < cols) {
+            const bool full = gxb + 3 < cols;
+            const int nc = cols - gxb;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ry = tr + 32 * h, gy = gyA + 32 * h;
+                if (ry >= halo && ry < R - halo && gy < rows) {
+                    const size_t off = (size_t)gy * o_u1.pitch + gxb;
+                    auto st = [&](const Plane &P, const f2 (&v)[4]) {
+                        if (h == 0) store_strip(P.p + off, v[0].x, v[1].x, v[2].x, v[3].x, full, nc);
+                        else store_strip(P.p + off, v[0].y, v[1].y, v[2].y, v[3].y, full, nc);
+                    };
+                    st(o_u1, r.u1);   st(o_u2, r.u2);
+                    st(o_p11, r.p11); st(o_p12, r.p12);
+                    st(o_p21, r.p21); st(o_p22, r.p22);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -457,8 +699,22 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
                    halo, tile, tiles_x, ntiles);
 }
 
-namespace {
-}  // namespace
+constexpr size_t smem_packed_bytes() { return sizeof(float) * (size_t)(N_IN * R * R) + sizeof(float4) * 4 * PEX_F4 + 64; }
+
+// halo rounded up to a multiple of 4 keeps every region origin 16-byte aligned (TMA box rule, vector stores)
+void tvl1_packed_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                        const Tvl1Scalars &k, int iters, int num_sms) {
+    const Tvl1State &so = B.s[cur ^ 1];
+    const int halo = (iters + 3) & ~3;
+    const int tile = R - 2 * halo;
+    const int tiles_x = div_up(cols, tile), tiles_y = div_up(rows, tile);
+    const int ntiles = tiles_x * tiles_y;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    const double bytes = 64.0 * (double)rows * cols * iters;
+    const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;  // the 64-wide box descriptors
+    B2F_LAUNCH(c, cls, bytes, k_tvl1_packed_tma, dim3(grid), dim3(NT), smem_packed_bytes(), *m, so.u1, so.u2, so.p11,
+               so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles);
+}
 
 cudaError_t tvl1_blocked_init() {
     static bool done[64] = {};
@@ -476,6 +732,9 @@ cudaError_t tvl1_blocked_init() {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_tma_bytes(R));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_packed_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_packed_bytes());
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }

@@ -79,6 +79,81 @@ __device__ __forceinline__ void tvl1_update_p(float taut, float ux, float uy, fl
     pb = __fmul_rn(__fmaf_rn(taut, uy, pb), inv);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed FP32 (Blackwell fma.rn.f32x2 / add.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FADD2 / FMUL2): the same
+// arithmetic on TWO independent pixels per instruction.  Every lane is an IEEE round-to-nearest
+// operation in the same order as the scalar functions above, so results are bit-identical to them;
+// the FP32 work of the iteration kernel takes half the issue slots.
+// ---------------------------------------------------------------------------------------------
+typedef float2 f2;
+__device__ __forceinline__ unsigned long long f2_pack(f2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ f2 f2_unpack(unsigned long long a) {
+    f2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
+    return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ f2 splat2(float v) { return make_float2(v, v); }
+
+// tvl1_update_u for two pixels.  ninv = -tvl1_inv_grad(grad): (-rho) * inv == rho * (-inv) bit for bit.
+__device__ __forceinline__ void tvl1_update_u_x2(const Tvl1Scalars &k, f2 Ix, f2 Iy, f2 ninv, f2 rho_c, f2 u1, f2 u2,
+                                                 f2 p11, f2 p11_l, f2 p12, f2 p12_u, f2 p21, f2 p21_l, f2 p22,
+                                                 f2 p22_u, f2 &u1n, f2 &u2n) {
+    const f2 rho = add2(rho_c, fma2(Iy, u2, mul2(Ix, u1)));
+    f2 fi = mul2(rho, ninv);
+    fi.x = fminf(fmaxf(fi.x, -k.l_t), k.l_t);
+    fi.y = fminf(fmaxf(fi.y, -k.l_t), k.l_t);
+    const f2 v1 = fma2(fi, Ix, u1);
+    const f2 v2 = fma2(fi, Iy, u2);
+    const f2 div1 = add2(sub2(p11, p11_l), sub2(p12, p12_u));
+    const f2 div2 = add2(sub2(p21, p21_l), sub2(p22, p22_u));
+    const f2 th = splat2(k.theta);
+    u1n = fma2(th, div1, v1);
+    u2n = fma2(th, div2, v2);
+}
+
+// tvl1_update_p2 for two pixels (the three MUFU per pixel stay scalar: there is no packed SFU op).
+__device__ __forceinline__ void tvl1_update_p2_x2(float taut, f2 ux1, f2 uy1, f2 ux2, f2 uy2, f2 &p11, f2 &p12,
+                                                  f2 &p21, f2 &p22) {
+    const f2 s1 = fma2(ux1, ux1, mul2(uy1, uy1));
+    const f2 s2 = fma2(ux2, ux2, mul2(uy2, uy2));
+    const f2 g1 = make_float2(sqrt_approx(s1.x), sqrt_approx(s1.y));
+    const f2 g2 = make_float2(sqrt_approx(s2.x), sqrt_approx(s2.y));
+    const f2 t = splat2(taut), one = splat2(1.0f);
+    const f2 a1 = fma2(t, g1, one);
+    const f2 a2 = fma2(t, g2, one);
+    const f2 m = mul2(a1, a2);
+    const f2 r = make_float2(rcp_approx(m.x), rcp_approx(m.y));
+    const f2 inv1 = mul2(r, a2), inv2 = mul2(r, a1);
+    p11 = mul2(fma2(t, ux1, p11), inv1);
+    p12 = mul2(fma2(t, uy1, p12), inv1);
+    p21 = mul2(fma2(t, ux2, p21), inv2);
+    p22 = mul2(fma2(t, uy2, p22), inv2);
+}
+
 // Keys bicubic kernel, a = -0.5 (tvl1flow.cu:89-104).
 __device__ __forceinline__ float bicubic_coeff(float x_) {
     const float x = fabsf(x_);

@@ -36,6 +36,12 @@ void parallel_for_(const Range &range, const ParallelLoopBody &body, double) {
 #endif
 }
 
+void Mat::first_touch(uchar *p, int rows, size_t step) {
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < rows; ++y)
+        for (size_t x = 0; x < step; x += 4096) p[(size_t)y * step + x] = 0;
+}
+
 // a contiguous copy of a (possibly ROI) float matrix
 static std::vector<float> dense(const Mat_<float> &m) {
     std::vector<float> v((size_t)m.rows * m.cols);

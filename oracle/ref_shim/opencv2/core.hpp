@@ -77,8 +77,9 @@ public:
         if (data && r == rows && c == cols && type == type_) return;
         rows = r; cols = c; type_ = type;
         step = (size_t)c * elemSize();
-        store_.reset(new std::vector<uchar>((size_t)r * step + 64));
-        data = store_->data();
+        store_.reset(new uchar[(size_t)r * step + 64], std::default_delete<uchar[]>());  // uninitialised, like cv::Mat
+        data = store_.get();
+        first_touch(data, r, step);
     }
     void create(Size s, int type) { create(s.height, s.width, type); }
     int type() const { return type_; }
@@ -102,7 +103,10 @@ public:
 
 protected:
     int type_ = 0;
-    std::shared_ptr<std::vector<uchar>> store_;
+    std::shared_ptr<uchar> store_;
+    // pages are faulted in by the OpenMP threads that will work on those rows (ref_glue.cpp: parallel_for_ uses the same
+    // static row partition), so the timed CPU baseline is NUMA-local like an OpenCV build with its own thread pool
+    static void first_touch(uchar *p, int rows, size_t step);
 };
 
 template <typename T> class Mat_;

@@ -50,3 +50,28 @@ if "tvl1" in WHAT:
         out.update({"kw_" + k: v for k, v in kw.items()})
         np.savez_compressed(os.path.join(HERE, f"tvl1_ref_{name}.npz"), **out)
         print("tvl1", name, flow.shape, float(np.abs(flow).mean()))
+
+
+def _model_fixture(name, I0, I1, flow, kw, seed, kind, dtype):
+    import hashlib
+    out = {"flow_s4": flow[::4, ::4].astype(np.float32), "shape": np.array(flow.shape[:2]), "seed": seed, "kind": kind,
+           "dtype": dtype, "sha1_I0": hashlib.sha1(np.ascontiguousarray(I0).tobytes()).hexdigest(),
+           "sha1_I1": hashlib.sha1(np.ascontiguousarray(I1).tobytes()).hexdigest(),
+           "mean_u": float(flow[..., 0].mean(dtype=np.float64)), "mean_v": float(flow[..., 1].mean(dtype=np.float64)),
+           "mean_abs": float(np.abs(flow).mean(dtype=np.float64))}
+    out.update({"kw_" + k: v for k, v in kw.items()})
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, flow.shape, out["mean_u"], out["mean_v"])
+
+
+if "brox" in WHAT:  # BASELINE configs[3]: 1280x720, create(0.197, 50, 0.8, 10, 77, 10) (cudaoptflow/test/test_optflow.cpp:75-76)
+    from oracle import brox_model  # noqa: E402
+    kw = dict(alpha=0.197, gamma=50.0, scale_factor=0.8, inner_iterations=10, outer_iterations=77, solver_iterations=10)
+    I0, I1, _ = synth.make_pair(720, 1280, seed=0, kind="smooth", dtype="f32")
+    _model_fixture("brox_720p.npz", I0, I1, brox_model.calc(I0, I1, brox_model.BroxParams(**kw)), kw, 0, "smooth", "f32")
+
+if "denselk" in WHAT:  # DensePyrLK defaults at 1080p: 13x13, maxLevel 3, 30 iterations (cudaoptflow.hpp:245-249)
+    from oracle import denselk_model  # noqa: E402
+    I0, I1, _ = synth.make_pair(1080, 1920, seed=0, kind="smooth")
+    flow = denselk_model.calc(I0, I1, (13, 13), 3, 30)
+    _model_fixture("denselk_1080p.npz", I0, I1, flow, dict(win_w=13, win_h=13, maxLevel=3, iters=30), 0, "smooth", "u8")

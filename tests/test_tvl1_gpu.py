@@ -50,7 +50,8 @@ def test_blocked_kernel_bit_identical_to_unfused(cuda_device, K):
     I0, I1, _ = synth.make_pair(203, 277, seed=3, kind="smooth")
     kw = dict(nscales=3, warps=2, epsilon=0.0, iterations=23)
     a, _ = _run(cuda_device, I0, I1, path=1, **kw)
-    for path in (0, 2):          # 0 = persistent TMA kernel, 2 = blocked kernel with plain loads
+    # 0 = packed-FP32 (f32x2) persistent TMA kernel, 4 = scalar persistent TMA kernel, 2 = blocked kernel, plain loads
+    for path in (0, 4, 2):
         for graph in (0, 1):
             b, _ = _run(cuda_device, I0, I1, path=path, fused=K, graph=graph, **kw)
             assert np.array_equal(a, b), (path, K, graph, float(np.abs(a - b).max()))
@@ -209,18 +210,66 @@ def test_1080p_round_trip_properties(cuda_device):
     assert np.array_equal(again, got)
 
 
+def _cpu_reference(I0, I1, P):
+    """The reference's own CPU source (oracle/_ref, built where /root/reference exists and shipped with the
+    snapshot) when present, else its bit-identical C port (tests/test_oracle_cpu.py pins one to the other)."""
+    from oracle import tvl1_cpu_native, tvl1_ref
+    if tvl1_ref.available():
+        return tvl1_ref.calc(I0, I1, P), "reference"
+    if tvl1_cpu_native.available():
+        return tvl1_cpu_native.calc(I0, I1, P), "port"
+    pytest.skip("neither oracle/_ref/libtvl1_ref.so nor oracle/_build/libtvl1_cpu.so is built")
+
+
+def test_engine_vs_golden_reference_vectors(cuda_device):
+    """tests/golden/tvl1_ref_*.npz: outputs of the reference's own modules/optflow/src/tvl1flow.cpp (compiled
+    unmodified, make_golden.py).  GPU parameters are the twin the reference's GPU-vs-CPU test uses
+    (test_optflow.cpp:456-460: iterations = inner * outer with inner = 1 ... here inner * outer in general);
+    acceptance = that test's NCC bound plus the CPU regression criterion (>= 95 % within 0.1 px)."""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    n = 0
+    for name in sorted(os.listdir(gold)):
+        if not (name.startswith("tvl1_ref_") and name.endswith(".npz")):
+            continue
+        z = np.load(os.path.join(gold, name))
+        kw = {k[3:]: z[k].item() for k in z.files if k.startswith("kw_")}
+        P = tvl1_cpu.TVL1Params(**kw)
+        if P.medianFiltering > 1 or P.epsilon > 0:
+            continue                  # the CUDA path has no median filter and a different (sampled) stopping rule
+        n += 1
+        got, _ = _run(cuda_device, z["I0"], z["I1"], nscales=P.nscales, warps=P.warps, epsilon=0.0,
+                      iterations=P.innerIterations * P.outerIterations, gamma=P.gamma)
+        st = metrics.epe_stats(got, z["flow"], border=16)
+        ncc = metrics.ncc_dissimilarity(got[16:-16, 16:-16], z["flow"][16:-16, 16:-16])
+        assert st["frac_le_0.1"] >= 0.95 and st["mean"] <= 0.08 and ncc <= 4e-3, (name, st, ncc)
+    assert n >= 2
+
+
+def test_4k_baseline_config_vs_cpu_oracle(cuda_device):
+    """BASELINE configs[4] frame size: 3840x2160, 5 scales / 10 warps / 30 iterations, eps = 0, one pair, against the
+    CPU reference (same tolerances as the 1080p test).  Levels 3840x2160 ... 1573x885."""
+    I0, I1, gt = synth.make_pair(2160, 3840, seed=0, kind="smooth")
+    got, alg = _run(cuda_device, I0, I1, nscales=5, warps=10, epsilon=0.0, iterations=30)
+    assert alg.getStats()["levels"] == 5 and np.isfinite(got).all()
+    cpu, kind = _cpu_reference(I0, I1, tvl1_cpu.TVL1Params(nscales=5, warps=10, epsilon=0.0, innerIterations=1,
+                                                           outerIterations=30, medianFiltering=1))
+    st = metrics.epe_stats(got, cpu, border=32)
+    ncc = metrics.ncc_dissimilarity(got[32:-32, 32:-32], cpu[32:-32, 32:-32])
+    assert st["frac_le_0.1"] >= 0.95 and st["mean"] <= 0.08 and ncc <= 4e-3, (kind, st, ncc)
+    g_gpu, g_cpu = metrics.epe_stats(got, gt, border=32), metrics.epe_stats(cpu, gt, border=32)
+    assert abs(g_gpu["mean"] - g_cpu["mean"]) <= 0.05, (g_gpu, g_cpu)
+
+
 def test_1080p_baseline_config_vs_cpu_oracle(cuda_device):
     """BASELINE configs[2] at full size: 1920x1080, 5 scales / 10 warps / 30 iterations, eps = 0, against the CPU
     oracle (the C/OpenMP port of modules/optflow/src/tvl1flow.cpp; a few seconds on the box's cores) at the
     reference's own GPU-vs-CPU acceptance level (test_optflow.cpp:456-465: NCC similarity; plus the regression
     criterion of test_tvl1optflow.cpp:114-142, >= 95 % of the pixels within 0.1 px)."""
-    from oracle import tvl1_cpu_native
-    if not tvl1_cpu_native.available():
-        pytest.skip("oracle/_build/libtvl1_cpu.so not built")
     I0, I1, gt = synth.make_pair(1080, 1920, seed=0, kind="smooth")
     got, _ = _run(cuda_device, I0, I1, nscales=5, warps=10, epsilon=0.0, iterations=30)
-    cpu = tvl1_cpu_native.calc(I0, I1, tvl1_cpu.TVL1Params(nscales=5, warps=10, epsilon=0.0, innerIterations=1,
-                                                           outerIterations=30, medianFiltering=1))
+    cpu, _kind = _cpu_reference(I0, I1, tvl1_cpu.TVL1Params(nscales=5, warps=10, epsilon=0.0, innerIterations=1,
+                                                            outerIterations=30, medianFiltering=1))
     st = metrics.epe_stats(got, cpu, border=32)
     ncc = metrics.ncc_dissimilarity(got[32:-32, 32:-32], cpu[32:-32, 32:-32])
     assert st["frac_le_0.1"] >= 0.95 and st["mean"] <= 0.08 and ncc <= 4e-3, (st, ncc)
