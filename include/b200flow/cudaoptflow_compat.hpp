@@ -26,6 +26,7 @@ namespace detail {
 using cv::Algorithm;
 using cv::InputArray;
 using cv::InputOutputArray;
+using cv::OutputArray;
 using cv::Ptr;
 using cv::Size;
 using cv::String;
@@ -33,10 +34,18 @@ using cv::cuda::GpuMat;
 using cv::cuda::Stream;
 template <class T, class... A> Ptr<T> make(A &&...a) { return cv::makePtr<T>(std::forward<A>(a)...); }
 inline GpuMat in_mat(InputArray a) { return a.getGpuMat(); }
-inline GpuMat out_mat(InputOutputArray a, Size sz, bool keep) {
+inline GpuMat &out_mat(InputOutputArray a, Size sz, bool keep) {
     if (!keep) a.create(sz, CV_32FC2);
     return a.getGpuMatRef();
 }
+inline cv::InputOutputArray noArray() { return cv::noArray(); }
+inline bool needed(OutputArray a) { return a.needed(); }
+// (re)allocate an output like the reference does (getOutputMat / create) and hand back the header
+inline GpuMat &out_create(OutputArray a, int rows, int cols, int type) {
+    a.create(rows, cols, type);
+    return a.getGpuMatRef();
+}
+inline GpuMat &out_ref(InputOutputArray a) { return a.getGpuMatRef(); }
 inline cudaStream_t raw(Stream &s) { return cv::cuda::StreamAccessor::getStream(s); }
 [[noreturn]] inline void fail(int status, const char *where) {
     const int code = status == B2F_CUDA_ERROR || status == B2F_OUT_OF_MEMORY ? cv::Error::GpuApiCallError
@@ -57,6 +66,13 @@ inline GpuMat &out_mat(InputOutputArray a, Size sz, bool keep) {
     if (!keep) a.create(sz, CV_32FC2);
     return a;
 }
+using shim::noArray;
+inline bool needed(OutputArray a) { return &a != &shim::noArray(); }
+inline GpuMat &out_create(OutputArray a, int rows, int cols, int type) {
+    a.create(rows, cols, type);
+    return a;
+}
+inline GpuMat &out_ref(InputOutputArray a) { return a; }
 inline cudaStream_t raw(Stream &s) { return s.cudaPtr(); }
 [[noreturn]] inline void fail(int status, const char *where) {
     const int code = status == B2F_CUDA_ERROR || status == B2F_OUT_OF_MEMORY ? -217 /*GpuApiCallError*/
@@ -74,6 +90,7 @@ using detail::Algorithm;
 using detail::GpuMat;
 using detail::InputArray;
 using detail::InputOutputArray;
+using detail::OutputArray;
 using detail::Ptr;
 using detail::Size;
 using detail::Stream;
@@ -238,26 +255,37 @@ public:
 
 #undef B2F_ACCESSOR
 
-/** cv::cuda::SparsePyrLKOpticalFlow (cudaoptflow.hpp:189-226).  prevPts / nextPts are 1 x N CV_32FC2, status
- *  1 x N CV_8UC1, err 1 x N CV_32FC1; nextPts, status and err are (re)allocated like the reference does
- *  (pyrlk.cpp:165,172,176).  `err` is a pointer here (nullptr = cv::noArray()). */
+/** cv::cuda::SparsePyrLKOpticalFlow (cudaoptflow.hpp:189-226), same signature as the reference's
+ *  SparseOpticalFlow::calc (:99-103): prevPts / nextPts are 1 x N CV_32FC2, status 1 x N CV_8UC1, err 1 x N CV_32FC1
+ *  and optional (`= cv::noArray()`); nextPts, status and err are (re)allocated like the reference does
+ *  (pyrlk.cpp:165,172,176). */
 class SparsePyrLKOpticalFlow : public Algorithm {
 public:
     ~SparsePyrLKOpticalFlow() { b2f_sparselk_destroy(h_); }
-    void calc(const GpuMat &prevImg, const GpuMat &nextImg, const GpuMat &prevPts, GpuMat &nextPts, GpuMat &status,
-              GpuMat *err = nullptr, Stream &stream = Stream::Null()) {
+    void calc(InputArray prevImg_, InputArray nextImg_, InputArray prevPts_, InputOutputArray nextPts_, OutputArray status_,
+              OutputArray err_ = detail::noArray(), Stream &stream = Stream::Null()) {
+        const auto &prevImg = detail::in_mat(prevImg_);
+        const auto &nextImg = detail::in_mat(nextImg_);
+        const auto &prevPts = detail::in_mat(prevPts_);
         if (prevPts.cols == 0) return;
         if (prevPts.rows != 1 || prevPts.type() != 13 /*CV_32FC2*/) detail::fail(B2F_BAD_ARG, "SparsePyrLKOpticalFlow::calc");
-        if (!getUseInitialFlow()) nextPts.create(1, prevPts.cols, 13);
-        else if (nextPts.cols != prevPts.cols || nextPts.type() != 13) detail::fail(B2F_SIZE_MISMATCH, "SparsePyrLKOpticalFlow::calc");
-        status.create(1, prevPts.cols, 0 /*CV_8UC1*/);
-        if (err) err->create(1, prevPts.cols, 5 /*CV_32FC1*/);
+        GpuMat *nextPts = &detail::out_ref(nextPts_);
+        if (!getUseInitialFlow()) nextPts = &detail::out_create(nextPts_, 1, prevPts.cols, 13);
+        else if (nextPts->cols != prevPts.cols || nextPts->type() != 13) detail::fail(B2F_SIZE_MISMATCH, "SparsePyrLKOpticalFlow::calc");
+        GpuMat &status = detail::out_create(status_, 1, prevPts.cols, 0 /*CV_8UC1*/);
+        GpuMat *err = detail::needed(err_) ? &detail::out_create(err_, 1, prevPts.cols, 5 /*CV_32FC1*/) : nullptr;
         b2f_image i0{prevImg.data, prevImg.step, prevImg.rows, prevImg.cols, prevImg.type()};
         b2f_image i1{nextImg.data, nextImg.step, nextImg.rows, nextImg.cols, nextImg.type()};
         const int st = b2f_sparselk_calc(h_, &i0, &i1, reinterpret_cast<const float *>(prevPts.data),
-                                         reinterpret_cast<float *>(nextPts.data), reinterpret_cast<unsigned char *>(status.data),
+                                         reinterpret_cast<float *>(nextPts->data), reinterpret_cast<unsigned char *>(status.data),
                                          err ? reinterpret_cast<float *>(err->data) : nullptr, prevPts.cols, detail::raw(stream));
         if (st != B2F_OK) detail::fail(st, "SparsePyrLKOpticalFlow::calc");
+    }
+    /** round-1 spelling: `err` as a pointer (nullptr = cv::noArray()) */
+    void calc(InputArray prevImg, InputArray nextImg, InputArray prevPts, InputOutputArray nextPts, OutputArray status,
+              GpuMat *err, Stream &stream = Stream::Null()) {
+        if (err) calc(prevImg, nextImg, prevPts, nextPts, status, *err, stream);
+        else calc(prevImg, nextImg, prevPts, nextPts, status, detail::noArray(), stream);
     }
     Size getWinSize() const { const auto p = params(); return Size(p.win_width, p.win_height); }
     void setWinSize(Size s) { auto p = params(); p.win_width = s.width; p.win_height = s.height; b2f_sparselk_set_params(h_, &p); }

@@ -96,6 +96,12 @@ public:
 
 typedef const GpuMat &InputArray;
 typedef GpuMat &InputOutputArray;
+typedef GpuMat &OutputArray;
+// cv::noArray(): the "not wanted" output; recognised by address
+inline GpuMat &noArray() {
+    static GpuMat none;
+    return none;
+}
 
 }  // namespace shim
 }  // namespace b200flow

@@ -721,7 +721,7 @@ size_t BroxEngine::layout(int rows, int cols, bool counting, Layout &L) {
 }
 
 cudaError_t BroxEngine::ensure_workspace(int rows, int cols) {
-    if (L_.rows == rows && L_.cols == cols && std::memcmp(&L_.P, &P, sizeof(P)) == 0 && arena.capacity() > 0)
+    if (L_.rows == rows && L_.cols == cols && same_params(L_.P, P) && arena.capacity() > 0)
         return cudaSuccess;
     Layout tmp;
     const size_t need = layout(rows, cols, true, tmp);
@@ -891,8 +891,8 @@ int BroxEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
 
     const bool want_graph = knobs.use_graph && !profiling && s != nullptr;
     if (want_graph) {
-        const bool hit = graph_exec_ && key_.rows == rows && key_.cols == cols && std::memcmp(&key_.P, &P, sizeof(P)) == 0 &&
-                         std::memcmp(&key_.knobs, &knobs, sizeof(knobs)) == 0 && key_.base == L_.levels[0].I0.p;
+        const bool hit = graph_exec_ && key_.rows == rows && key_.cols == cols && same_params(key_.P, P) &&
+                         same_knobs(key_.knobs, knobs) && key_.base == L_.levels[0].I0.p;
         if (!hit) {
             destroy_graph();
             cudaStream_t cs = nullptr;

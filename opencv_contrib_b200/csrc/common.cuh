@@ -147,11 +147,41 @@ struct EngineKnobs {
     int kernel_path = 0;  // 0 auto, 1 unfused reference-shaped kernels
 };
 
+// Field-wise equality of the public parameter structs (they contain padding after int members, so memcmp on
+// copies may see indeterminate bytes and miss a cache hit).
+static inline bool same_params(const b2f_tvl1_params &a, const b2f_tvl1_params &b) {
+    return a.tau == b.tau && a.lambda == b.lambda && a.theta == b.theta && a.nscales == b.nscales && a.warps == b.warps &&
+           a.epsilon == b.epsilon && a.iterations == b.iterations && a.scale_step == b.scale_step && a.gamma == b.gamma &&
+           a.use_initial_flow == b.use_initial_flow;
+}
+static inline bool same_params(const b2f_farneback_params &a, const b2f_farneback_params &b) {
+    return a.num_levels == b.num_levels && a.pyr_scale == b.pyr_scale && a.fast_pyramids == b.fast_pyramids &&
+           a.win_size == b.win_size && a.num_iters == b.num_iters && a.poly_n == b.poly_n && a.poly_sigma == b.poly_sigma &&
+           a.flags == b.flags;
+}
+static inline bool same_params(const b2f_brox_params &a, const b2f_brox_params &b) {
+    return a.alpha == b.alpha && a.gamma == b.gamma && a.scale_factor == b.scale_factor &&
+           a.inner_iterations == b.inner_iterations && a.outer_iterations == b.outer_iterations &&
+           a.solver_iterations == b.solver_iterations;
+}
+static inline bool same_knobs(const EngineKnobs &a, const EngineKnobs &b) {
+    return a.fused_iters == b.fused_iters && a.use_graph == b.use_graph && a.kernel_path == b.kernel_path;
+}
+
 }  // namespace b2f
 
 struct b2f_handle {
     int algo = 0;
     int last_cuda_error = 0;
+    // A handle belongs to the device of its first call (arena, CUDA graph, TMA descriptors and the SM count are
+    // created there): a later call whose stream / images live on another device is refused with B2F_BAD_ARG.
+    int device = -1;
+    bool bind_device() {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return true; }
+        if (device < 0) device = cur;
+        return device == cur;
+    }
     b2f_stats stats{};
     bool profiling = false;
     b2f::EngineKnobs knobs;
@@ -185,6 +215,8 @@ struct b2f_handle {
     virtual const char *default_name() const = 0;
     virtual const char *class_name(int cls) const = 0;
     virtual size_t workspace_bytes(int rows, int cols, int type) = 0;
+    // does calc() read the caller's `flow` before writing it (useInitialFlow / OPTFLOW_USE_INITIAL_FLOW)?
+    virtual bool reads_flow() const { return false; }
 
     b2f::Ctx make_ctx(cudaStream_t s);
     int finish(b2f::Ctx &ctx, cudaStream_t s);  // maps ctx.err -> status, NULL-stream sync

@@ -295,6 +295,8 @@ public:
         Layout L;
         return layout(rows, cols, true, L);
     }
+    // rejected pixels are never written (pyrlk.cu:709-855): what the caller's flow held stays visible
+    bool reads_flow() const override { return true; }
 
 private:
     struct Layout {

@@ -876,6 +876,7 @@ public:
         std::vector<float> tabs;
         return layout(rows, cols, true, L, tabs);
     }
+    bool reads_flow() const override { return (P.flags & B2F_OPTFLOW_USE_INITIAL_FLOW) != 0; }
 
 private:
     struct Layout {
@@ -893,7 +894,8 @@ private:
     Layout L_;
 
     size_t layout(int rows, int cols, bool counting, Layout &L, std::vector<float> &tabs);
-    cudaError_t ensure_workspace(int rows, int cols);
+    cudaError_t ensure_workspace(int rows, int cols, cudaStream_t s);
+    std::vector<float> tabs_host_;  // source of the asynchronous table upload
 };
 
 size_t FarnebackEngine::layout(int rows, int cols, bool counting, Layout &L, std::vector<float> &tabs) {
@@ -976,18 +978,24 @@ size_t FarnebackEngine::layout(int rows, int cols, bool counting, Layout &L, std
     return A.used();
 }
 
-cudaError_t FarnebackEngine::ensure_workspace(int rows, int cols) {
-    if (L_.rows == rows && L_.cols == cols && std::memcmp(&L_.P, &P, sizeof(P)) == 0 && arena.capacity() > 0)
+cudaError_t FarnebackEngine::ensure_workspace(int rows, int cols, cudaStream_t s) {
+    if (L_.rows == rows && L_.cols == cols && same_params(L_.P, P) && arena.capacity() > 0)
         return cudaSuccess;
     Layout tmp;
     std::vector<float> tabs;
     const size_t need = layout(rows, cols, true, tmp, tabs);
     cudaError_t e = arena.reserve(need);
     if (e != cudaSuccess) return e;
+    // Re-layout of a live arena (new size or parameters on the same handle): kernels of the previous call may still be
+    // reading it on the caller's stream, and the table upload below must be ordered against them too.
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
     layout(rows, cols, false, L_, tabs);
     if (!prepare_poly_tabs(P.poly_n, P.poly_sigma, L_.poly)) return cudaErrorInvalidValue;
-    // one-time synchronous table upload (the reference re-uploads __constant__ tables every call)
-    return cudaMemcpy(L_.tabs_dev, tabs.data(), sizeof(float) * tabs.size(), cudaMemcpyHostToDevice);
+    // one-time table upload on the call's stream (the reference re-uploads __constant__ tables every call); the host copy
+    // lives in the handle so the asynchronous copy never reads a dead buffer
+    tabs_host_ = tabs;
+    return cudaMemcpyAsync(L_.tabs_dev, tabs_host_.data(), sizeof(float) * tabs_host_.size(), cudaMemcpyHostToDevice, s);
 }
 
 int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, cudaStream_t s) {
@@ -1006,7 +1014,7 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
 
     const int rows = I0->rows, cols = I0->cols;
     Ctx c = make_ctx(s);
-    c.check(ensure_workspace(rows, cols));
+    c.check(ensure_workspace(rows, cols, s));
     if (!c.ok()) return finish(c, s);
     {
         static bool attr_done[64] = {};

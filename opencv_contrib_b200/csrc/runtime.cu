@@ -166,6 +166,7 @@ int b2f_calc(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_image 
     if (st != B2F_OK) return st;
     h->stats.calls++;
     b2f::DeviceScope dev(I0->data, static_cast<cudaStream_t>(cuda_stream));
+    if (!h->bind_device()) return B2F_BAD_ARG;
     return h->calc(I0, I1, flow, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -179,6 +180,7 @@ int b2f_calc_uv(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_ima
     if (v->rows != u->rows || v->cols != u->cols) return B2F_SIZE_MISMATCH;
     h->stats.calls++;
     b2f::DeviceScope dev(I0->data, static_cast<cudaStream_t>(cuda_stream));
+    if (!h->bind_device()) return B2F_BAD_ARG;
     h->planar_v = v->data;
     h->planar_v_step = v->step;
     st = h->calc(I0, I1, u, static_cast<cudaStream_t>(cuda_stream));
@@ -205,9 +207,12 @@ int b2f_calc_host(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_i
     if (fs != 8) return B2F_UNSUPPORTED_TYPE;
     if (I1->rows != I0->rows || I1->cols != I0->cols || flow->rows != I0->rows || flow->cols != I0->cols)
         return B2F_SIZE_MISMATCH;
+    const int rows = I0->rows, cols = I0->cols;
+    // a short pitch is a caller error, not a CUDA failure
+    if (I0->step < cols * es || I1->step < cols * es || flow->step < cols * fs) return B2F_BAD_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     b2f::DeviceScope dev(nullptr, s);  // host buffers: the stream names the device
-    const int rows = I0->rows, cols = I0->cols;
+    if (!h->bind_device()) return B2F_BAD_ARG;
     size_t in_pitch = (cols * es + 255) & ~size_t(255);
     size_t fl_pitch = (cols * fs + 255) & ~size_t(255);
     size_t need = 2 * in_pitch * rows + fl_pitch * rows;
@@ -231,10 +236,8 @@ int b2f_calc_host(b2f_handle *h, const b2f_image *I0, const b2f_image *I1, b2f_i
         e = cudaMemcpy2DAsync(d1, in_pitch, I1->data, I1->step, cols * es, rows, cudaMemcpyHostToDevice, s);
     b2f_image g0{d0, in_pitch, rows, cols, I0->type}, g1{d1, in_pitch, rows, cols, I1->type};
     b2f_image gf{df, fl_pitch, rows, cols, B2F_32FC2};
-    if (e == cudaSuccess) {
-        // use-initial-flow paths read the caller's flow first
+    if (e == cudaSuccess && h->reads_flow())  // only the use-initial-flow paths read the caller's flow (8 B/px of H2D)
         e = cudaMemcpy2DAsync(df, fl_pitch, flow->data, flow->step, cols * fs, rows, cudaMemcpyHostToDevice, s);
-    }
     if (e != cudaSuccess) {
         h->last_cuda_error = e;
         cudaGetLastError();

@@ -253,6 +253,7 @@ public:
         Layout L;
         return layout(rows, cols, true, L);
     }
+    bool reads_flow() const override { return P.use_initial_flow != 0; }
 
 private:
     struct Layout {
@@ -611,8 +612,8 @@ int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
     const bool want_graph = knobs.use_graph && fixed_schedule && !profiling && s != nullptr;
     if (want_graph) {
         const bool hit = graph_exec_ && graph_key_.rows == rows && graph_key_.cols == cols &&
-                         std::memcmp(&graph_key_.P, &P, sizeof(P)) == 0 &&
-                         std::memcmp(&graph_key_.knobs, &knobs, sizeof(knobs)) == 0 &&
+                         same_params(graph_key_.P, P) &&
+                         same_knobs(graph_key_.knobs, knobs) &&
                          graph_key_.base == L_.levels[0].I0.p;
         if (!hit) {
             destroy_graph();

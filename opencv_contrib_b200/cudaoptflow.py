@@ -69,6 +69,11 @@ class DenseOpticalFlow:
     """cv::cuda::DenseOpticalFlow (cudaoptflow.hpp:70-81)."""
 
     _family = ""
+    _keeps_stale_flow = False  # DensePyrLK never writes rejected pixels: an omitted `flow` is allocated zeroed
+
+    def _needs_initial_flow(self) -> bool:
+        """True when calc() reads the caller's flow first (useInitialFlow / OPTFLOW_USE_INITIAL_FLOW)."""
+        return False
 
     def __init__(self, handle):
         self._h = handle
@@ -88,7 +93,10 @@ class DenseOpticalFlow:
         """calc(I0, I1, flow[, stream]) -> flow  (cudaoptflow.hpp:80).  Asynchronous on ``stream``."""
         torch = _torch()
         if flow is None:
-            flow = torch.empty((I0.shape[0], I0.shape[1], 2), dtype=torch.float32, device=I0.device)
+            if self._needs_initial_flow():  # the reference asserts a valid flow of matching size (tvl1flow.cpp:190)
+                raise B2FError(1)
+            alloc = torch.zeros if self._keeps_stale_flow else torch.empty
+            flow = alloc((I0.shape[0], I0.shape[1], 2), dtype=torch.float32, device=I0.device)
         i0, i1, fl = _image_from_tensor(I0), _image_from_tensor(I1), _image_from_tensor(flow, True)
         if stream is None:
             stream = torch.cuda.current_stream(I0.device)
@@ -102,6 +110,8 @@ class DenseOpticalFlow:
         """Planar variant: calc + cuda::split in one call (b2f_calc_uv; the reference's consumers split
         the CV_32FC2 result themselves, superres/src/optical_flow.cpp:557-574).  Returns (u, v)."""
         torch = _torch()
+        if (u is None or v is None) and self._needs_initial_flow():
+            raise B2FError(1)
         if u is None:
             u = torch.empty((I0.shape[0], I0.shape[1]), dtype=torch.float32, device=I0.device)
         if v is None:
@@ -118,6 +128,8 @@ class DenseOpticalFlow:
 
     def calc_host(self, I0: np.ndarray, I1: np.ndarray, flow: np.ndarray | None = None, stream=None):
         """Host-buffer variant (upload + calc + download inside the call; b2f_calc_host)."""
+        if flow is None and self._needs_initial_flow():
+            raise B2FError(1)
         if flow is None:
             flow = np.zeros((I0.shape[0], I0.shape[1], 2), np.float32)
         i0, i1, fl = _image_from_numpy(I0), _image_from_numpy(I1), _image_from_numpy(flow, True)
@@ -190,6 +202,9 @@ def _accessors(cls, family: str, table):
 class OpticalFlowDual_TVL1(DenseOpticalFlow):
     """cv::cuda::OpticalFlowDual_TVL1 (cudaoptflow.hpp:305-386)."""
 
+    def _needs_initial_flow(self) -> bool:
+        return bool(self.getUseInitialFlow())
+
 
 _accessors(OpticalFlowDual_TVL1, "tvl1", {
     "tau": ("Tau", float), "lambda_": ("Lambda", float), "theta": ("Theta", float),
@@ -200,6 +215,9 @@ _accessors(OpticalFlowDual_TVL1, "tvl1", {
 
 class FarnebackOpticalFlow(DenseOpticalFlow):
     """cv::cuda::FarnebackOpticalFlow (cudaoptflow.hpp:258-294)."""
+
+    def _needs_initial_flow(self) -> bool:
+        return (int(self.getFlags()) & OPTFLOW_USE_INITIAL_FLOW) != 0
 
 
 _accessors(FarnebackOpticalFlow, "farneback", {
@@ -220,6 +238,7 @@ _accessors(BroxOpticalFlow, "brox", {
 
 class DensePyrLKOpticalFlow(DenseOpticalFlow):
     """cv::cuda::DensePyrLKOpticalFlow (cudaoptflow.hpp:230-250)."""
+    _keeps_stale_flow = True
 
     def getWinSize(self):
         return (int(self._get(PARAM["denselk"]["win_width"])), int(self._get(PARAM["denselk"]["win_height"])))

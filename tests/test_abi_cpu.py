@@ -95,3 +95,20 @@ def test_header_is_plain_c99(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
                         "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_cpp_adapter_real_opencv_branch_compiles(tmp_path):
+    """include/b200flow/cudaoptflow_compat.hpp selects its real-OpenCV branch whenever OpenCV's core headers are on
+    the include path; the image has none, so that branch is compiled here (syntax only) against declaration-only
+    stand-ins that keep opencv core's signatures (getGpuMat() by value, getGpuMatRef() by reference, cv::noArray())."""
+    import shutil
+    import subprocess
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if not gxx or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no C++ compiler / CUDA headers")
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-DB200FLOW_WITH_OPENCV", "-I", os.path.join(cpp, "opencv_stub"),
+                        "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, os.path.join(cpp, "opencv_branch_syntax.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

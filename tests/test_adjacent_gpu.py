@@ -199,6 +199,12 @@ def test_entry_points_follow_the_stream_device_not_the_thread_device(cuda_device
     t.join()
     assert "err" not in out, out.get("err")
     assert np.array_equal(out["host"], ref) and np.array_equal(out["dev"], ref)
+    # a handle belongs to the device of its first call: reuse on another device is refused, not silently run
+    alg = ocb.FarnebackOpticalFlow_create(numLevels=3)
+    alg.calc_host(I0, I1)                                 # binds to device 0
+    with pytest.raises(ocb.B2FError) as e:
+        alg.calc(torch.from_numpy(I0).to(d1), torch.from_numpy(I1).to(d1), torch.empty((96, 128, 2), device=d1))
+    assert e.value.status == 1
 
 
 @pytest.mark.parametrize("family,params,dt", [

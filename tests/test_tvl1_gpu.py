@@ -193,6 +193,20 @@ def test_error_codes(cuda_device):
     with pytest.raises(ocb.B2FError) as e:
         alg.calc(a, a)
     assert e.value.status == 1                                    # nscales > 0 (tvl1flow.cpp:191)
+    alg = ocb.OpticalFlowDual_TVL1_create(useInitialFlow=True)
+    with pytest.raises(ocb.B2FError) as e:
+        alg.calc(a, a)                                            # initial flow requested but none supplied (:190)
+    assert e.value.status == 1
+    with pytest.raises(ocb.B2FError) as e:                        # short host pitch is a bad argument, not a CUDA error
+        import ctypes as C
+        from opencv_contrib_b200 import _lib
+        h = np.zeros((64, 64), np.uint8)
+        f = np.zeros((64, 64, 2), np.float32)
+        i0 = _lib.b2f_image(h.ctypes.data, 32, 64, 64, 0)
+        fl = _lib.b2f_image(f.ctypes.data, 512, 64, 64, 13)
+        st = _lib.lib().b2f_calc_host(ocb.OpticalFlowDual_TVL1_create()._h, C.byref(i0), C.byref(i0), C.byref(fl), None)
+        raise ocb.B2FError(st)
+    assert e.value.status == 1
 
 
 def test_1080p_round_trip_properties(cuda_device):
