@@ -145,8 +145,11 @@ typedef enum b2f_param_id {
     /* engine knobs (no reference counterpart) */
     B2F_ENGINE_FUSED_ITERS = 900, /* TV-L1: inner iterations fused per HBM pass (0 = auto)     */
     B2F_ENGINE_USE_GRAPH = 901,   /* capture the fixed schedule in a CUDA graph (default 1)    */
-    B2F_ENGINE_KERNEL_PATH = 902  /* TV-L1: 0 = auto (persistent TMA kernel), 1 = unfused
-                                     reference-shaped kernels, 2 = blocked kernel without TMA   */
+    B2F_ENGINE_KERNEL_PATH = 902, /* TV-L1: 0 = auto (packed-FP32 persistent TMA kernel), 1 = unfused
+                                     reference-shaped kernels, 2 = blocked kernel without TMA,
+                                     4 = scalar persistent TMA kernel (3: without elect.sync)   */
+    B2F_ENGINE_AUX_PATH = 903     /* TV-L1: 0 = separable warp kernel, 1 = tap-by-tap warp kernel
+                                     (accumulation in the reference's order)                     */
 } b2f_param_id;
 
 B2F_API int b2f_set_param(b2f_handle *h, int id, double value);

@@ -139,7 +139,7 @@ PARAM = {
     "brox": dict(alpha=300, gamma=301, scale_factor=302, inner_iterations=303, outer_iterations=304,
                  solver_iterations=305),
     "denselk": dict(win_width=400, win_height=401, max_level=402, iters=403, use_initial_flow=404),
-    "engine": dict(fused_iters=900, use_graph=901, kernel_path=902),
+    "engine": dict(fused_iters=900, use_graph=901, kernel_path=902, aux_path=903),
 }
 
 _lib = None

@@ -145,6 +145,7 @@ struct EngineKnobs {
     int fused_iters = 0;  // 0 = auto
     int use_graph = 1;
     int kernel_path = 0;  // 0 auto, 1 unfused reference-shaped kernels
+    int aux_path = 0;     // variant of the secondary kernels (TV-L1: 0 separable warp, 1 tap-by-tap warp)
 };
 
 // Field-wise equality of the public parameter structs (they contain padding after int members, so memcmp on
@@ -165,7 +166,8 @@ static inline bool same_params(const b2f_brox_params &a, const b2f_brox_params &
            a.solver_iterations == b.solver_iterations;
 }
 static inline bool same_knobs(const EngineKnobs &a, const EngineKnobs &b) {
-    return a.fused_iters == b.fused_iters && a.use_graph == b.use_graph && a.kernel_path == b.kernel_path;
+    return a.fused_iters == b.fused_iters && a.use_graph == b.use_graph && a.kernel_path == b.kernel_path &&
+           a.aux_path == b.aux_path;
 }
 
 }  // namespace b2f
@@ -224,6 +226,62 @@ struct b2f_handle {
 };
 
 namespace b2f {
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-graph cache of a fixed launch schedule (one per handle).  capture() records whatever `body` launches
+// through the Ctx it is given -- on a private capture stream -- and remembers the launch / byte accounting, so a
+// replay updates b2f_stats exactly like the eager path would.
+// ---------------------------------------------------------------------------------------------
+struct GraphCache {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;
+    uint64_t class_launches[B2F_MAX_KERNEL_CLASSES] = {};
+    double class_bytes[B2F_MAX_KERNEL_CLASSES] = {};
+    int iterations = 0;
+    ~GraphCache() { destroy(); }
+    void destroy() {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+    }
+    template <class Body>
+    void capture(b2f_handle &h, Ctx &c, Body &&body) {
+        destroy();
+        cudaStream_t cs = nullptr;
+        c.check(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        if (!c.ok()) return;
+        Ctx g = h.make_ctx(cs);
+        b2f_stats scratch = h.stats;  // capture must not double-count launches
+        scratch.iterations_run = 0;
+        g.stats = &scratch;
+        g.capturing = true;
+        g.profiling = false;
+        g.check(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        if (g.ok()) body(g);
+        cudaGraph_t graph = nullptr;
+        g.check(cudaStreamEndCapture(cs, &graph));
+        if (g.ok() && graph) g.check(cudaGraphInstantiate(&exec, graph, 0));
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        launches = scratch.launches - h.stats.launches;
+        for (int i = 0; i < B2F_MAX_KERNEL_CLASSES; ++i) {
+            class_launches[i] = scratch.class_launches[i] - h.stats.class_launches[i];
+            class_bytes[i] = scratch.class_bytes[i] - h.stats.class_bytes[i];
+        }
+        iterations = scratch.iterations_run;
+        c.check(g.err);
+        if (!c.ok()) destroy();
+    }
+    void replay(b2f_handle &h, Ctx &c, cudaStream_t s) {
+        if (!c.ok() || !exec) return;
+        c.check(cudaGraphLaunch(exec, s));
+        h.stats.launches += launches;
+        for (int i = 0; i < B2F_MAX_KERNEL_CLASSES; ++i) {
+            h.stats.class_launches[i] += class_launches[i];
+            h.stats.class_bytes[i] += class_bytes[i];
+        }
+        h.stats.iterations_run = iterations;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Shared kernels (pyramid.cu)

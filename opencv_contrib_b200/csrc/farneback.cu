@@ -893,6 +893,16 @@ private:
     };
     Layout L_;
 
+    // the whole fixed schedule between the conversion of the caller's frames and the final merge, as one CUDA graph
+    GraphCache graph_;
+    struct GraphKey {
+        int rows = 0, cols = 0;
+        b2f_farneback_params P{};
+        EngineKnobs knobs;
+        void *base = nullptr;
+    } graph_key_;
+    void solve(Ctx &c);
+
     size_t layout(int rows, int cols, bool counting, Layout &L, std::vector<float> &tabs);
     cudaError_t ensure_workspace(int rows, int cols, cudaStream_t s);
     std::vector<float> tabs_host_;  // source of the asynchronous table upload
@@ -1047,13 +1057,45 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
     const dim3 block(32, 8);
 
     convert_pair(c, CLS_IMG, v0, v1, L.frames[0], L.frames[1], 1.0f);  // convertTo(CV_32F), farneback.cpp:342-345
+    if (P.flags & B2F_OPTFLOW_USE_INITIAL_FLOW) split_flow(c, CLS_FLOW, vf, L.levels[0].fx, L.levels[0].fy);
+
+    // Every launch below works on arena planes only, so the schedule is captured once per (size, parameters) and
+    // replayed: one graph launch instead of ~90 kernel launches per pair (the coarse levels are launch-bound).
+    const bool want_graph = knobs.use_graph && !profiling && s != nullptr;
+    if (want_graph) {
+        const bool hit = graph_.exec && graph_key_.rows == rows && graph_key_.cols == cols &&
+                         same_params(graph_key_.P, P) && same_knobs(graph_key_.knobs, knobs) &&
+                         graph_key_.base == L.frames[0].p;
+        if (!hit) {
+            graph_.capture(*this, c, [&](Ctx &g) { solve(g); });
+            if (c.ok()) {
+                graph_key_.rows = rows;
+                graph_key_.cols = cols;
+                graph_key_.P = P;
+                graph_key_.knobs = knobs;
+                graph_key_.base = L.frames[0].p;
+            }
+        }
+        graph_.replay(*this, c, s);
+    } else {
+        solve(c);
+    }
+
+    merge_flow(c, CLS_FLOW, L.levels[0].fx, L.levels[0].fy, vf);  // farneback.cpp:197-198
+    return finish(c, s);
+}
+
+void FarnebackEngine::solve(Ctx &c) {
+    Layout &L = L_;
+    const int rows = L.rows, cols = L.cols;
+    const int top = static_cast<int>(L.levels.size()) - 1;
+    const dim3 block(32, 8);
     if (P.fast_pyramids) {
         for (int k = 1; k <= top; ++k)
             for (int i = 0; i < 2; ++i)
                 pyr_down(c, CLS_IMG, L.levels[k - 1].img[i], L.levels[k - 1].rows, L.levels[k - 1].cols,
                          L.levels[k].img[i], L.levels[k].rows, L.levels[k].cols);
     }
-    if (P.flags & B2F_OPTFLOW_USE_INITIAL_FLOW) split_flow(c, CLS_FLOW, vf, L.levels[0].fx, L.levels[0].fy);
 
     const int khalf = P.win_size / 2;
     const float box_inv = 1.f / ((1 + 2 * khalf) * (1 + 2 * khalf));
@@ -1172,12 +1214,9 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
             Ma = Mb;
             Mb = t;
             a_is_input = !a_is_input;
-            stats.iterations_run++;
+            c.stats->iterations_run++;
         }
     }
-
-    merge_flow(c, CLS_FLOW, L.levels[0].fx, L.levels[0].fy, vf);  // farneback.cpp:197-198
-    return finish(c, s);
 }
 
 int FarnebackEngine::set_param(int id, double v) {

@@ -137,6 +137,7 @@ int b2f_set_param(b2f_handle *h, int id, double value) {
         case B2F_ENGINE_FUSED_ITERS: h->knobs.fused_iters = static_cast<int>(value); return B2F_OK;
         case B2F_ENGINE_USE_GRAPH: h->knobs.use_graph = value != 0; return B2F_OK;
         case B2F_ENGINE_KERNEL_PATH: h->knobs.kernel_path = static_cast<int>(value); return B2F_OK;
+        case B2F_ENGINE_AUX_PATH: h->knobs.aux_path = static_cast<int>(value); return B2F_OK;
         default: return h->set_param(id, value);
     }
 }
@@ -147,6 +148,7 @@ int b2f_get_param(const b2f_handle *h, int id, double *value) {
         case B2F_ENGINE_FUSED_ITERS: *value = h->knobs.fused_iters; return B2F_OK;
         case B2F_ENGINE_USE_GRAPH: *value = h->knobs.use_graph; return B2F_OK;
         case B2F_ENGINE_KERNEL_PATH: *value = h->knobs.kernel_path; return B2F_OK;
+        case B2F_ENGINE_AUX_PATH: *value = h->knobs.aux_path; return B2F_OK;
         default: return h->get_param(id, value);
     }
 }

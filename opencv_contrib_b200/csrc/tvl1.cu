@@ -117,6 +117,89 @@ __global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p
     rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
 }
 
+// Keys a = -0.5 weights of the four taps at distances (1 + t, t, 1 - t, 2 - t), t in [0, 1): the polynomials of
+// bicubic_coeff expanded in t (same values up to rounding; t itself is exact, the reference rounds t + 1 and 2 - t).
+__device__ __forceinline__ void keys_weights(float t, float (&k)[4]) {
+    k[0] = ((-0.5f * t + 1.0f) * t - 0.5f) * t;
+    k[1] = (1.5f * t - 2.5f) * t * t + 1.0f;
+    k[2] = ((-1.5f * t + 2.0f) * t + 0.5f) * t;
+    k[3] = (0.5f * t - 0.5f) * t * t;
+}
+
+// Separable form of the same warp (round 2, the default): w_ij = kx[i] * ky[j], so the three weighted sums are row
+// sums r[j] = sum_i kx[i] W[j][i+1] (6 rows), rx[j] = sum_i kx[i] (W[j][i+2] - W[j][i]) (4 rows) combined with ky:
+//   I1w = sum_j ky[j] r[j+1],  I1wx = 0.5 sum_j ky[j] rx[j+1],  I1wy = 0.5 sum_j ky[j] (r[j+2] - r[j]),
+// about half the arithmetic of the tap-by-tap form (which stays available as aux_path 1 and for the few pixels whose
+// window touches the image border).  Results differ from the tap-by-tap accumulation by rounding only.
+__global__ void __launch_bounds__(256) k_tvl1_warp_sep(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
+                                                       Plane grad, Plane rho, int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+
+    const float u1 = u1p.at(y, x);
+    const float u2 = u2p.at(y, x);
+    const float wx = x + u1;
+    const float wy = y + u2;
+    const float fx = floorf(wx), fy = floorf(wy);
+    const int ix = static_cast<int>(fminf(fmaxf(fx, -8.f), cols + 8.f)) - 1;
+    const int iy = static_cast<int>(fminf(fmaxf(fy, -8.f), rows + 8.f)) - 1;
+
+    float kx[4], ky[4];
+    keys_weights(wx - fx, kx);
+    keys_weights(wy - fy, ky);
+    float sum, sumx, sumy;
+    const float wsum = ((kx[0] + kx[1]) + (kx[2] + kx[3])) * ((ky[0] + ky[1]) + (ky[2] + ky[3]));
+
+    if (ix >= 1 && iy >= 1 && ix + 4 <= cols - 1 && iy + 4 <= rows - 1) {
+        const float *base = &I1.at(iy - 1, ix - 1);
+        float r[6], rx[4];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float *row = base + (size_t)j * I1.pitch;
+            const float a1 = __ldg(row + 1), a2 = __ldg(row + 2), a3 = __ldg(row + 3), a4 = __ldg(row + 4);
+            r[j] = __fmaf_rn(kx[3], a4, __fmaf_rn(kx[2], a3, __fmaf_rn(kx[1], a2, kx[0] * a1)));
+            if (j >= 1 && j <= 4) {
+                const float a0 = __ldg(row), a5 = __ldg(row + 5);
+                rx[j - 1] = __fmaf_rn(kx[3], a5 - a3, __fmaf_rn(kx[2], a4 - a2, __fmaf_rn(kx[1], a3 - a1, kx[0] * (a2 - a0))));
+            }
+        }
+        sum = __fmaf_rn(ky[3], r[4], __fmaf_rn(ky[2], r[3], __fmaf_rn(ky[1], r[2], ky[0] * r[1])));
+        sumx = 0.5f * __fmaf_rn(ky[3], rx[3], __fmaf_rn(ky[2], rx[2], __fmaf_rn(ky[1], rx[1], ky[0] * rx[0])));
+        sumy = 0.5f * __fmaf_rn(ky[3], r[5] - r[3], __fmaf_rn(ky[2], r[4] - r[2], __fmaf_rn(ky[1], r[3] - r[1], ky[0] * (r[2] - r[0]))));
+    } else {
+        // border: clamp every tap, then take the clamped-neighbour gradient at the clamped tap
+        sum = 0.f; sumx = 0.f; sumy = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cy = clampi(iy + j, 0, rows - 1);
+            const int cyp = min(cy + 1, rows - 1), cym = max(cy - 1, 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cx = clampi(ix + i, 0, cols - 1);
+                const int cxp = min(cx + 1, cols - 1), cxm = max(cx - 1, 0);
+                const float w = kx[i] * ky[j];
+                const float v = __ldg(&I1.at(cy, cx));
+                const float gx = 0.5f * (__ldg(&I1.at(cy, cxp)) - __ldg(&I1.at(cy, cxm)));
+                const float gy = 0.5f * (__ldg(&I1.at(cyp, cx)) - __ldg(&I1.at(cym, cx)));
+                sum = __fmaf_rn(w, v, sum);
+                sumx = __fmaf_rn(w, gx, sumx);
+                sumy = __fmaf_rn(w, gy, sumy);
+            }
+        }
+    }
+
+    const float coeff = 1.0f / wsum;
+    const float I1w = sum * coeff;
+    const float Ix = sumx * coeff;
+    const float Iy = sumy * coeff;
+    I1wx.at(y, x) = Ix;
+    I1wy.at(y, x) = Iy;
+    grad.at(y, x) = __fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix));
+    const float I0v = I0.at(y, x);
+    rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Unfused, reference-shaped inner iteration (any gamma, optional error image reduction).
 // Used for gamma != 0, for the epsilon > 0 cadence and as the cross-check for the blocked kernel.
@@ -482,8 +565,12 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
 
     for (int w = 0; w < P.warps; ++w) {
         point_T_at(cur);
-        B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy,
-                   T.grad, T.rho_c, rows, cols);
+        if (knobs.aux_path == 1)  // tap-by-tap accumulation in the reference's order
+            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy,
+                       T.grad, T.rho_c, rows, cols);
+        else
+            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_sep, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx,
+                       T.I1wy, T.grad, T.rho_c, rows, cols);
 
         if (blocked_ok && !(P.epsilon > 0.0)) {  // fixed schedule
             run_blocked(P.iterations);
