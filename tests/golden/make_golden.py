@@ -4,8 +4,8 @@
   tvl1_ref_*.npz   the reference's OWN CPU Dual TV-L1, /root/reference/modules/optflow/src/tvl1flow.cpp compiled
                    unmodified into oracle/_ref/libtvl1_ref.so (oracle/Makefile, oracle/ref_shim/)
   brox_720p.npz, denselk_1080p.npz   BASELINE-size outputs of the numpy restatements oracle/brox_model.py and
-                   oracle/denselk_model.py (no CPU implementation exists upstream: "parity unpinned"), stored as float16
-                   on a stride-4 grid plus full-resolution summary statistics -- minutes of numpy per case
+                   oracle/denselk_model.py (no CPU implementation exists upstream: "parity unpinned"), stored as float32
+                   on a stride-4 grid plus full-resolution means -- 2 minutes (brox) / 27 minutes (denselk) of numpy
 python tests/golden/make_golden.py [farneback] [tvl1] [brox] [denselk]      (no argument = farneback + tvl1)"""
 import os
 import sys
