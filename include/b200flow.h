@@ -133,6 +133,17 @@ typedef enum b2f_param_id {
     B2F_TVL1_TAU = 100, B2F_TVL1_LAMBDA, B2F_TVL1_THETA, B2F_TVL1_NSCALES, B2F_TVL1_WARPS,
     B2F_TVL1_EPSILON, B2F_TVL1_ITERATIONS, B2F_TVL1_SCALE_STEP, B2F_TVL1_GAMMA,
     B2F_TVL1_USE_INITIAL_FLOW,
+    /* TV-L1 knobs of the reference's CPU / OpenCL class (cv::optflow::DualTVL1OpticalFlow), set through b2f_set_param
+     * only -- cv::cuda::OpticalFlowDual_TVL1::create has no such arguments:
+     *   MEDIAN_FILTERING  1 = off (default), 3 or 5: cv::medianBlur of (u1, u2) before every block of MEDIAN_PERIOD
+     *                     iterations (modules/optflow/src/tvl1flow.cpp:1377-1383);
+     *   MEDIAN_PERIOD     iterations between two median passes = the CPU path's innerIterations (0 = once per warp);
+     *                     CPU twin of (inner I, outer O, median k) = iterations I*O, MEDIAN_PERIOD I, MEDIAN_FILTERING k.
+     *   INITIAL_FLOW_SOURCE  what useInitialFlow starts from: 0 = the caller's `flow` (default), 1 = this handle's own
+     *                     previous result (zero on a fresh handle) -- the reference's CUDA class never reads the caller's
+     *                     flow: it takes flowx / flowy from the buffer pool (src/tvl1flow.cpp:175-179,203-207), i.e.
+     *                     whatever the previous call left there. */
+    B2F_TVL1_MEDIAN_FILTERING = 120, B2F_TVL1_MEDIAN_PERIOD, B2F_TVL1_INITIAL_FLOW_SOURCE,
     /* Farneback */
     B2F_FARN_NUM_LEVELS = 200, B2F_FARN_PYR_SCALE, B2F_FARN_FAST_PYRAMIDS, B2F_FARN_WIN_SIZE,
     B2F_FARN_NUM_ITERS, B2F_FARN_POLY_N, B2F_FARN_POLY_SIGMA, B2F_FARN_FLAGS,
@@ -151,6 +162,11 @@ typedef enum b2f_param_id {
     B2F_ENGINE_AUX_PATH = 903     /* TV-L1: 0 = separable warp kernel, 1 = tap-by-tap warp kernel
                                      (accumulation in the reference's order)                     */
 } b2f_param_id;
+
+/* cv::medianBlur for CV_32FC1, ksize 3 or 5, replicated border, not in place: the primitive behind
+ * B2F_TVL1_MEDIAN_FILTERING (the reference's CPU path calls cv::medianBlur, modules/optflow/src/tvl1flow.cpp:1381-1382;
+ * cv::cuda has no float median filter).  Pitched device planes (step a multiple of 4 bytes). */
+B2F_API int b2f_median_blur_32f(const b2f_image *src, b2f_image *dst, int ksize, void *cuda_stream);
 
 B2F_API int b2f_set_param(b2f_handle *h, int id, double value);
 B2F_API int b2f_get_param(const b2f_handle *h, int id, double *value);

@@ -77,6 +77,7 @@ SYMBOLS = [
     ("b2f_brox_default_params", None, [C.POINTER(b2f_brox_params)]),
     ("b2f_denselk_default_params", None, [C.POINTER(b2f_denselk_params)]),
     ("b2f_tvl1_create", C.c_int, [C.POINTER(b2f_tvl1_params), C.POINTER(_H)]),
+    ("b2f_median_blur_32f", C.c_int, [C.POINTER(b2f_image), C.POINTER(b2f_image), C.c_int, C.c_void_p]),
     ("b2f_farneback_create", C.c_int, [C.POINTER(b2f_farneback_params), C.POINTER(_H)]),
     ("b2f_brox_create", C.c_int, [C.POINTER(b2f_brox_params), C.POINTER(_H)]),
     ("b2f_denselk_create", C.c_int, [C.POINTER(b2f_denselk_params), C.POINTER(_H)]),
@@ -133,7 +134,8 @@ SYMBOLS = [
 # b2f_param_id values (include/b200flow.h)
 PARAM = {
     "tvl1": dict(tau=100, lambda_=101, theta=102, nscales=103, warps=104, epsilon=105, iterations=106,
-                 scale_step=107, gamma=108, use_initial_flow=109),
+                 scale_step=107, gamma=108, use_initial_flow=109,
+                 median_filtering=120, median_period=121, initial_flow_source=122),
     "farneback": dict(num_levels=200, pyr_scale=201, fast_pyramids=202, win_size=203, num_iters=204,
                       poly_n=205, poly_sigma=206, flags=207),
     "brox": dict(alpha=300, gamma=301, scale_factor=302, inner_iterations=303, outer_iterations=304,

@@ -15,6 +15,7 @@
 #include "tvl1_math.cuh"
 #include "tvl1_blocked.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -289,6 +290,40 @@ __global__ void __launch_bounds__(256) k_tvl1_estimate_dual(Tvl1Planes P, int ro
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// cv::medianBlur on the flow planes (float, 3x3 / 5x5, replicated border): the knob of the reference's CPU / OpenCL
+// Dual TV-L1 (modules/optflow/src/tvl1flow.cpp:1379-1383, :1266-1269), absent from its CUDA class.  Exact median
+// (the reference's float path is a sorting network): partial selection sort of the window up to the middle element.
+// Two planes per launch (z = 0: u1, z = 1: u2).
+// ---------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) k_tvl1_median(Plane a_in, Plane b_in, Plane a_out, Plane b_out, int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const Plane src = blockIdx.z ? b_in : a_in;
+    const Plane dst = blockIdx.z ? b_out : a_out;
+    constexpr int R = KS / 2, N = KS * KS;
+    float w[N];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+        const int yy = clampi(y + j - R, 0, rows - 1);
+#pragma unroll
+        for (int i = 0; i < KS; ++i) w[j * KS + i] = __ldg(&src.at(yy, clampi(x + i - R, 0, cols - 1)));
+    }
+    // the (N/2)-th smallest: after pass k the k smallest sit in w[0..k]
+#pragma unroll
+    for (int k = 0; k <= N / 2; ++k) {
+#pragma unroll
+        for (int q = k + 1; q < N; ++q) {
+            const float lo = fminf(w[k], w[q]), hi = fmaxf(w[k], w[q]);
+            w[k] = lo;
+            w[q] = hi;
+        }
+    }
+    dst.at(y, x) = w[N / 2];
+}
+
 // Fixed-order final reduction of the per-block partial sums (single block).
 __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, int n,
                                                          double *__restrict__ out) {
@@ -322,6 +357,10 @@ public:
     }
 
     b2f_tvl1_params P;
+    // knobs without a counterpart in cv::cuda::OpticalFlowDual_TVL1::create (b2f_set_param only):
+    int median_filtering = 1;     // cv::optflow::DualTVL1OpticalFlow::medianFiltering: 1 = off, 3 or 5 = kernel size
+    int median_period = 0;        // iterations between two median passes (= the CPU path's innerIterations); 0 = once per warp
+    int initial_flow_source = 0;  // useInitialFlow reads: 0 the caller's flow, 1 this handle's previous result (see set_param)
 
     int calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, cudaStream_t s) override;
     int set_param(int id, double v) override;
@@ -336,7 +375,7 @@ public:
         Layout L;
         return layout(rows, cols, true, L);
     }
-    bool reads_flow() const override { return P.use_initial_flow != 0; }
+    bool reads_flow() const override { return P.use_initial_flow != 0 && initial_flow_source == 0; }
 
 private:
     struct Layout {
@@ -368,6 +407,7 @@ private:
         int rows = 0, cols = 0, type = -1;
         b2f_tvl1_params P{};
         EngineKnobs knobs;
+        int median_filtering = 1, median_period = 0;
         void *base = nullptr;
     } graph_key_;
     uint64_t graph_launches_ = 0;
@@ -450,6 +490,10 @@ cudaError_t Tvl1Engine::ensure_workspace(int rows, int cols) {
     cudaError_t e = arena.reserve(need);
     if (e != cudaSuccess) return e;
     layout(rows, cols, false, L_);
+    // initial_flow_source 1 starts from a zero field on a fresh workspace
+    e = cudaMemset(L_.levels[0].u1.p, 0, sizeof(float) * (size_t)L_.levels[0].u1.pitch * rows);
+    if (e == cudaSuccess) e = cudaMemset(L_.levels[0].u2.p, 0, sizeof(float) * (size_t)L_.levels[0].u2.pitch * rows);
+    if (e != cudaSuccess) return e;
     if (!err_host) e = cudaMallocHost(&err_host, sizeof(double) * 4);
     if (e != cudaSuccess) return e;
     // TMA descriptors for every solved level and both ping-pong directions
@@ -563,6 +607,21 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
         c.stats->iterations_run += count;
     };
 
+    // median pass on the current (u1, u2): into the spare state set's planes, then back (the p planes stay put)
+    const int med_k = (median_filtering == 3 || median_filtering == 5) ? median_filtering : 1;
+    const int med_period = median_period > 0 ? median_period : (P.iterations > 0 ? P.iterations : 1);
+    auto median_pass = [&]() {
+        point_T_at(cur);
+        Plane s1 = blocked_ok ? B.s[cur ^ 1].u1 : shared_plane(SH_U1B, cols);
+        Plane s2 = blocked_ok ? B.s[cur ^ 1].u2 : shared_plane(SH_U2B, cols);
+        const dim3 gm(grid.x, grid.y, 2);
+        if (med_k == 3)
+            B2F_LAUNCH(c, CLS_PROLONG, 16.0 * npx, k_tvl1_median<3>, gm, block, 0, T.u1, T.u2, s1, s2, rows, cols);
+        else
+            B2F_LAUNCH(c, CLS_PROLONG, 16.0 * npx, k_tvl1_median<5>, gm, block, 0, T.u1, T.u2, s1, s2, rows, cols);
+        resize_linear_pair(c, CLS_PROLONG, s1, s2, rows, cols, T.u1, T.u2, rows, cols, 1.f, 1.f, 1.f);
+    };
+
     for (int w = 0; w < P.warps; ++w) {
         point_T_at(cur);
         if (knobs.aux_path == 1)  // tap-by-tap accumulation in the reference's order
@@ -573,7 +632,14 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
                        T.I1wy, T.grad, T.rho_c, rows, cols);
 
         if (blocked_ok && !(P.epsilon > 0.0)) {  // fixed schedule
-            run_blocked(P.iterations);
+            if (med_k == 1) {
+                run_blocked(P.iterations);
+            } else {  // the CPU path's outer loop: median, then `period` inner iterations (tvl1flow.cpp:1377-1404)
+                for (int done = 0; done < P.iterations; done += med_period) {
+                    median_pass();
+                    run_blocked(std::min(med_period, P.iterations - done));
+                }
+            }
             continue;
         }
 
@@ -582,13 +648,15 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
         double prevError = 0.0;
         int n = 0;
         while (error > scaledEpsilon && n < P.iterations) {
+            if (med_k > 1 && n % med_period == 0) median_pass();
             const bool calcError = (P.epsilon > 0) && (n & 1) && (prevError < scaledEpsilon);
             if (!calcError && blocked_ok) {
                 // count the unsampled iterations ahead (each of them leaves error = DBL_MAX and
                 // prevError -= scaledEpsilon) and run them as one blocked stretch
                 int m = 0;
                 double pe = prevError;
-                while (n + m < P.iterations && !((P.epsilon > 0) && ((n + m) & 1) && (pe < scaledEpsilon))) {
+                while (n + m < P.iterations && !((P.epsilon > 0) && ((n + m) & 1) && (pe < scaledEpsilon)) &&
+                       !(med_k > 1 && m > 0 && (n + m) % med_period == 0)) {
                     pe -= scaledEpsilon;
                     ++m;
                 }
@@ -682,7 +750,8 @@ int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
 
     // convertTo(CV_32F, 8U ? 1 : 255), tvl1flow.cpp:200-201
     convert_pair(c, CLS_PYR, v0, v1, L_.levels[0].I0, L_.levels[0].I1, I0->type == B2F_8UC1 ? 1.0f : 255.0f);
-    if (P.use_initial_flow) split_flow(c, CLS_PROLONG, vf, L_.levels[0].u1, L_.levels[0].u2);
+    // initial_flow_source 1: the level-0 planes still hold this handle's previous result (zero after a re-layout)
+    if (P.use_initial_flow && initial_flow_source == 0) split_flow(c, CLS_PROLONG, vf, L_.levels[0].u1, L_.levels[0].u2);
 
     // image (and initial-flow) pyramid, tvl1flow.cpp:238-266
     const int built = static_cast<int>(L_.levels.size());
@@ -700,7 +769,8 @@ int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
     if (want_graph) {
         const bool hit = graph_exec_ && graph_key_.rows == rows && graph_key_.cols == cols &&
                          same_params(graph_key_.P, P) &&
-                         same_knobs(graph_key_.knobs, knobs) &&
+                         same_knobs(graph_key_.knobs, knobs) && graph_key_.median_filtering == median_filtering &&
+                         graph_key_.median_period == median_period &&
                          graph_key_.base == L_.levels[0].I0.p;
         if (!hit) {
             destroy_graph();
@@ -731,6 +801,8 @@ int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
                     graph_key_.cols = cols;
                     graph_key_.P = P;
                     graph_key_.knobs = knobs;
+                    graph_key_.median_filtering = median_filtering;
+                    graph_key_.median_period = median_period;
                     graph_key_.base = L_.levels[0].I0.p;
                 } else {
                     destroy_graph();
@@ -767,6 +839,20 @@ int Tvl1Engine::set_param(int id, double v) {
         case B2F_TVL1_SCALE_STEP: P.scale_step = v; break;
         case B2F_TVL1_GAMMA: P.gamma = v; break;
         case B2F_TVL1_USE_INITIAL_FLOW: P.use_initial_flow = v != 0; break;
+        case B2F_TVL1_MEDIAN_FILTERING: {
+            const int k = static_cast<int>(v);
+            if (!(k == 1 || k == 3 || k == 5)) return B2F_BAD_ARG;  // cv::medianBlur on CV_32F takes 3 and 5 only
+            median_filtering = k;
+            break;
+        }
+        case B2F_TVL1_MEDIAN_PERIOD:
+            if (v < 0) return B2F_BAD_ARG;
+            median_period = static_cast<int>(v);
+            break;
+        case B2F_TVL1_INITIAL_FLOW_SOURCE:
+            if (!(v == 0 || v == 1)) return B2F_BAD_ARG;
+            initial_flow_source = static_cast<int>(v);
+            break;
         default: return B2F_BAD_ARG;
     }
     return B2F_OK;
@@ -784,6 +870,9 @@ int Tvl1Engine::get_param(int id, double *v) const {
         case B2F_TVL1_SCALE_STEP: *v = P.scale_step; break;
         case B2F_TVL1_GAMMA: *v = P.gamma; break;
         case B2F_TVL1_USE_INITIAL_FLOW: *v = P.use_initial_flow; break;
+        case B2F_TVL1_MEDIAN_FILTERING: *v = median_filtering; break;
+        case B2F_TVL1_MEDIAN_PERIOD: *v = median_period; break;
+        case B2F_TVL1_INITIAL_FLOW_SOURCE: *v = initial_flow_source; break;
         default: return B2F_BAD_ARG;
     }
     return B2F_OK;
@@ -807,6 +896,25 @@ void b2f_tvl1_default_params(b2f_tvl1_params *p) {
     p->scale_step = 0.8;
     p->gamma = 0.0;
     p->use_initial_flow = 0;
+}
+
+int b2f_median_blur_32f(const b2f_image *src, b2f_image *dst, int ksize, void *cuda_stream) {
+    using namespace b2f;
+    if (!src || !dst || !src->data || !dst->data) return B2F_BAD_ARG;
+    if (src->type != B2F_32FC1 || dst->type != B2F_32FC1) return B2F_UNSUPPORTED_TYPE;
+    if (src->rows != dst->rows || src->cols != dst->cols) return B2F_SIZE_MISMATCH;
+    if (!(ksize == 3 || ksize == 5) || src->rows <= 0 || src->cols <= 0 || (src->step % 4) || (dst->step % 4) ||
+        src->step < (size_t)src->cols * 4 || dst->step < (size_t)dst->cols * 4 || src->data == dst->data)
+        return B2F_BAD_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+    DeviceScope dev(src->data, s);
+    const Plane a{static_cast<float *>(src->data), (int)(src->step / 4)}, b{static_cast<float *>(dst->data), (int)(dst->step / 4)};
+    const dim3 block(32, 8), grid(div_up(src->cols, 32), div_up(src->rows, 8), 1);
+    if (ksize == 3) k_tvl1_median<3><<<grid, block, 0, s>>>(a, a, b, b, src->rows, src->cols);
+    else k_tvl1_median<5><<<grid, block, 0, s>>>(a, a, b, b, src->rows, src->cols);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && s == nullptr) e = cudaDeviceSynchronize();
+    return e == cudaSuccess ? B2F_OK : B2F_CUDA_ERROR;
 }
 
 int b2f_tvl1_create(const b2f_tvl1_params *p, b2f_handle **out) {

@@ -203,14 +203,17 @@ class OpticalFlowDual_TVL1(DenseOpticalFlow):
     """cv::cuda::OpticalFlowDual_TVL1 (cudaoptflow.hpp:305-386)."""
 
     def _needs_initial_flow(self) -> bool:
-        return bool(self.getUseInitialFlow())
+        return bool(self.getUseInitialFlow()) and self.getInitialFlowSource() == 0
 
 
 _accessors(OpticalFlowDual_TVL1, "tvl1", {
     "tau": ("Tau", float), "lambda_": ("Lambda", float), "theta": ("Theta", float),
     "nscales": ("NumScales", int), "warps": ("NumWarps", int), "epsilon": ("Epsilon", float),
     "iterations": ("NumIterations", int), "scale_step": ("ScaleStep", float), "gamma": ("Gamma", float),
-    "use_initial_flow": ("UseInitialFlow", bool)})
+    "use_initial_flow": ("UseInitialFlow", bool),
+    # knobs of the reference's CPU / OpenCL class (cv::optflow::DualTVL1OpticalFlow), see include/b200flow.h
+    "median_filtering": ("MedianFiltering", int), "median_period": ("MedianPeriod", int),
+    "initial_flow_source": ("InitialFlowSource", int)})
 
 
 class FarnebackOpticalFlow(DenseOpticalFlow):

@@ -23,7 +23,7 @@ CASES = {
     "gauss": (dict(flags=256), 2e-2, 0.2),
     "scale08": (dict(pyrScale=0.8, numLevels=3), 1e-4, 0.02),
 }
-WHAT = set(sys.argv[1:]) or {"farneback", "tvl1"}
+WHAT = {a.split(":", 1)[0] for a in sys.argv[1:]} or {"farneback", "tvl1"}   # "tvl1:<case>" regenerates one TV-L1 case
 for name, (kw, ncc_tol, epe_tol) in (CASES.items() if "farneback" in WHAT else ()):
     I0, I1, _ = synth.make_pair(144, 192, seed=11, kind="smooth")
     flow = cv2.calcOpticalFlowFarneback(I0, I1, None, kw.get("pyrScale", 0.5), kw.get("numLevels", 5), 13, 10,
@@ -42,8 +42,13 @@ if "tvl1" in WHAT:
         "defaults": dict(),                                             # median 5, eps 0.01, 10 x 30
         "gamma": dict(gamma=0.5, medianFiltering=1, epsilon=0.0, innerIterations=5, outerIterations=4),
         "f32_median3": dict(medianFiltering=3, warps=2),
+        # fixed work with the median filter on: what the engine's MEDIAN_FILTERING / MEDIAN_PERIOD knobs are checked against
+        "median5_fixed": dict(nscales=3, warps=3, epsilon=0.0, innerIterations=10, outerIterations=3, medianFiltering=5),
     }
+    only = {a.split(":", 1)[1] for a in sys.argv[1:] if a.startswith("tvl1:")}
     for name, kw in TV.items():
+        if only and name not in only:
+            continue
         I0, I1, gt = synth.make_pair(120, 160, seed=21, kind="affine", dtype="f32" if name.startswith("f32") else "u8")
         flow = tvl1_ref.calc(I0, I1, tvl1_cpu.TVL1Params(**kw))
         out = {"I0": I0, "I1": I1, "flow": flow, "gt": gt.astype(np.float32), "source": tvl1_ref.source()}

@@ -18,10 +18,13 @@ from oracle import synth, metrics, tvl1_cpu, tvl1_gpu_model as gm
 pytestmark = pytest.mark.gpu
 
 
-def _run(dev, I0, I1, path=0, fused=0, graph=1, stream=None, init=None, **kw):
+def _run(dev, I0, I1, path=0, fused=0, graph=1, stream=None, init=None, _median=None, **kw):
     import torch
     import opencv_contrib_b200 as ocb
     alg = ocb.OpticalFlowDual_TVL1_create(**kw)
+    if _median is not None:
+        alg.setMedianFiltering(_median[0])
+        alg.setMedianPeriod(_median[1])
     alg.setEngineOption("kernel_path", path)
     alg.setEngineOption("fused_iters", fused)
     alg.setEngineOption("use_graph", graph)
@@ -249,15 +252,52 @@ def test_engine_vs_golden_reference_vectors(cuda_device):
         z = np.load(os.path.join(gold, name))
         kw = {k[3:]: z[k].item() for k in z.files if k.startswith("kw_")}
         P = tvl1_cpu.TVL1Params(**kw)
-        if P.medianFiltering > 1 or P.epsilon > 0:
-            continue                  # the CUDA path has no median filter and a different (sampled) stopping rule
+        if P.epsilon > 0:
+            continue                  # the CUDA path samples its stopping rule on another cadence (tvl1flow.cpp:357-380)
         n += 1
         got, _ = _run(cuda_device, z["I0"], z["I1"], nscales=P.nscales, warps=P.warps, epsilon=0.0,
-                      iterations=P.innerIterations * P.outerIterations, gamma=P.gamma)
+                      iterations=P.innerIterations * P.outerIterations, gamma=P.gamma,
+                      _median=(P.medianFiltering, P.innerIterations))
         st = metrics.epe_stats(got, z["flow"], border=16)
         ncc = metrics.ncc_dissimilarity(got[16:-16, 16:-16], z["flow"][16:-16, 16:-16])
         assert st["frac_le_0.1"] >= 0.95 and st["mean"] <= 0.08 and ncc <= 4e-3, (name, st, ncc)
-    assert n >= 2
+    assert n >= 3
+
+
+def test_median_filtering_knob_and_initial_flow_source(cuda_device):
+    """MEDIAN_FILTERING / MEDIAN_PERIOD (the CPU / OpenCL class's medianFiltering, tvl1flow.cpp:1377-1383): a pass with
+    kernel 5 must change the result, kernel 1 must not, the median kernel itself is the exact cv2.medianBlur; and
+    INITIAL_FLOW_SOURCE 1 (the reference CUDA class's de-facto behaviour) equals feeding the previous result back."""
+    import cv2
+    import torch
+    import opencv_contrib_b200 as ocb
+    I0, I1, _ = synth.make_pair(120, 160, seed=3, kind="smooth")
+    kw = dict(nscales=1, warps=1, epsilon=0.0, iterations=4)
+    base, _ = _run(cuda_device, I0, I1, **kw)
+    same, _ = _run(cuda_device, I0, I1, _median=(1, 2), **kw)
+    med, _ = _run(cuda_device, I0, I1, _median=(5, 2), **kw)
+    assert np.array_equal(base, same) and not np.array_equal(base, med)
+    # the primitive itself is the exact cv2.medianBlur (pitched planes)
+    import ctypes as C
+    from opencv_contrib_b200 import _lib
+    from opencv_contrib_b200.cudaoptflow import _image_from_tensor
+    a = np.random.default_rng(0).normal(0, 2, (97, 131)).astype(np.float32)
+    src = torch.zeros((97, 160), device=cuda_device)
+    src[:, :131] = torch.from_numpy(a).to(cuda_device)
+    for k in (3, 5):
+        dst = torch.zeros((97, 131), device=cuda_device)
+        si, di = _image_from_tensor(src[:, :131]), _image_from_tensor(dst, True)
+        assert _lib.lib().b2f_median_blur_32f(C.byref(si), C.byref(di), k, None) == 0
+        assert np.array_equal(dst.cpu().numpy(), cv2.medianBlur(a, k)), k
+    # initial-flow source 1: second call starts from the first call's result
+    d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
+    alg = ocb.OpticalFlowDual_TVL1_create(nscales=1, warps=2, epsilon=0.0, iterations=10, useInitialFlow=True)
+    alg.setInitialFlowSource(1)
+    first = alg.calc(d0, d1).cpu().numpy()                       # fresh handle: starts from zero
+    second = alg.calc(d0, d1).cpu().numpy()
+    ref0, _ = _run(cuda_device, I0, I1, nscales=1, warps=2, epsilon=0.0, iterations=10)
+    ref1, _ = _run(cuda_device, I0, I1, init=ref0, nscales=1, warps=2, epsilon=0.0, iterations=10, useInitialFlow=True)
+    assert np.array_equal(first, ref0) and np.array_equal(second, ref1)
 
 
 def test_4k_baseline_config_vs_cpu_oracle(cuda_device):
