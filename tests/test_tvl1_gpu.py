@@ -286,7 +286,7 @@ def test_median_filtering_knob_and_initial_flow_source(cuda_device):
     src[:, :131] = torch.from_numpy(a).to(cuda_device)
     for k in (3, 5):
         dst = torch.zeros((97, 131), device=cuda_device)
-        si, di = _image_from_tensor(src[:, :131]), _image_from_tensor(dst, True)
+        si, di = _image_from_tensor(src[:, :131]), _image_from_tensor(dst)
         assert _lib.lib().b2f_median_blur_32f(C.byref(si), C.byref(di), k, None) == 0
         assert np.array_equal(dst.cpu().numpy(), cv2.medianBlur(a, k)), k
     # initial-flow source 1: second call starts from the first call's result
