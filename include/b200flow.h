@@ -43,7 +43,12 @@ typedef enum b2f_status {
 enum {
     B2F_8UC1 = 0,   /* CV_8UC1  */
     B2F_32FC1 = 5,  /* CV_32FC1 */
-    B2F_32FC2 = 13  /* CV_32FC2 */
+    B2F_32FC2 = 13, /* CV_32FC2 */
+    /* accepted by b2f_sparselk_calc only (the instantiations of cuda/pyrlk.cu's dispatcher table, src/pyrlk.cpp:195-203):
+     * depth 8U / 16U / 32S / 32F with 1, 3 or 4 interleaved channels */
+    B2F_16UC1 = 2, B2F_32SC1 = 4,
+    B2F_8UC3 = 16, B2F_16UC3 = 18, B2F_32SC3 = 20, B2F_32FC3 = 21,
+    B2F_8UC4 = 24, B2F_16UC4 = 26, B2F_32SC4 = 28, B2F_32FC4 = 29
 };
 
 /* Mirror of the GpuMat fields that cross the boundary (data/step/rows/cols/type). `data` is a

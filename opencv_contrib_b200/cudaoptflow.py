@@ -293,6 +293,25 @@ def DensePyrLKOpticalFlow_create(winSize=(13, 13), maxLevel=3, iters=30, useInit
     return _create(DensePyrLKOpticalFlow, "b2f_denselk_create", p)
 
 
+def _sparse_image(t) -> b2f_image:
+    """(H, W) or (H, W, C) CUDA tensor, C in {1, 3, 4}, dtype uint8 / uint16 / int32 / float32 -> b2f_image with OpenCV's
+    CV_MAKETYPE(depth, C) flag: the instantiations of the reference's sparse dispatcher table (pyrlk.cpp:195-203)."""
+    torch = _torch()
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("expected a CUDA torch.Tensor (the GpuMat stand-in)")
+    depth = {torch.uint8: 0, torch.uint16: 2, torch.int32: 4, torch.float32: 5}.get(t.dtype)
+    if depth is None or t.dim() not in (2, 3):
+        raise B2FError(2)
+    cn = 1 if t.dim() == 2 else int(t.shape[2])
+    if cn not in (1, 3, 4):
+        raise B2FError(2)  # CV_Assert(channels == 1 || 3 || 4), pyrlk.cpp:228
+    if t.dim() == 3 and (t.stride(2) != 1 or t.stride(1) != cn):
+        raise ValueError("pixels must be interleaved and contiguous")
+    if t.dim() == 2 and t.stride(1) != 1:
+        raise ValueError("image rows must be contiguous")
+    return b2f_image(t.data_ptr(), t.stride(0) * t.element_size(), t.shape[0], t.shape[1], depth + ((cn - 1) << 3))
+
+
 class SparsePyrLKOpticalFlow:
     """cv::cuda::SparsePyrLKOpticalFlow (cudaoptflow.hpp:189-226).
 
@@ -365,7 +384,7 @@ class SparsePyrLKOpticalFlow:
             status = torch.empty((n,), dtype=torch.uint8, device=prevPts.device)
         if err is None and wantErr:
             err = torch.empty((n,), dtype=torch.float32, device=prevPts.device)
-        i0, i1 = _image_from_tensor(prevImg), _image_from_tensor(nextImg)
+        i0, i1 = _sparse_image(prevImg), _sparse_image(nextImg)
         if stream is None:
             stream = torch.cuda.current_stream(prevImg.device)
         sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)

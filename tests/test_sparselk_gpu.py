@@ -91,3 +91,66 @@ def test_sparse_pyrlk_edge_cases(cuda_device):
     # empty input -> empty output, no error (pyrlk.cpp:221-227)
     e, s, _ = alg.calc(d0, d1, torch.empty((0, 2), dtype=torch.float32, device=cuda_device))
     assert e.numel() == 0 and s.numel() == 0
+
+
+def _color_pair(h, w, seed, kind):
+    """Three-channel pair: each channel is an independent texture warped by the SAME flow."""
+    chans0, chans1 = [], []
+    for c in range(3):
+        a, b, gt = synth.make_pair(h, w, seed=seed + 31 * c, kind=kind)
+        chans0.append(a)
+        chans1.append(b)
+    return np.stack(chans0, -1), np.stack(chans1, -1), gt
+
+
+@pytest.mark.parametrize("depth,cn", [("u8", 3), ("u8", 4), ("u16", 1), ("u16", 3), ("u16", 4), ("s32", 1), ("s32", 3),
+                                      ("s32", 4), ("f32", 3), ("f32", 4)])
+def test_sparse_pyrlk_other_depths_and_channels(cuda_device, depth, cn):
+    """The other instantiations of the reference's dispatcher table (pyrlk.cpp:195-203): 16U / 32S and 3 / 4 channels,
+    through their own sampling paths (texture vs software bilinear, see csrc/sparselk.cu).  Oracle: the live CPU
+    cv2.calcOpticalFlowPyrLK on the 8-bit image of the same content (it takes 8-bit input only), the reference's own
+    criterion (<= 1 % of the points differ in status or by more than one pixel, test_optflow.cpp:241-264).  A fourth
+    channel is a copy of the first (cv2 runs on the same 4-channel image)."""
+    import torch
+    import opencv_contrib_b200 as ocb
+    if cn == 1:
+        I0, I1, gt = synth.make_pair(300, 400, seed=23, kind="affine")
+        g0, g1 = I0, I1
+    else:
+        I0, I1, gt = _color_pair(300, 400, 23, "affine")
+        if cn == 4:
+            I0, I1 = np.concatenate([I0, I0[..., :1]], -1), np.concatenate([I1, I1[..., :1]], -1)
+        g0, g1 = np.ascontiguousarray(I0), np.ascontiguousarray(I1)
+    mask = np.zeros(I0.shape[:2], np.uint8)
+    mask[12:-12, 12:-12] = 255
+    gray = I0 if cn == 1 else np.ascontiguousarray(I0[..., 0])
+    pts = cv2.goodFeaturesToTrack(gray, 600, 0.01, 0.0, mask=mask).reshape(-1, 2).astype(np.float32)
+    assert len(pts) > 200
+    gold, st_gold, _ = cv2.calcOpticalFlowPyrLK(g0, g1, pts.reshape(-1, 1, 2), None)
+    gold, st_gold = gold.reshape(-1, 2), st_gold.ravel()
+    np_t = {"u8": np.uint8, "u16": np.uint16, "s32": np.int32, "f32": np.float32}[depth]
+    d0 = torch.from_numpy(np.ascontiguousarray(I0.astype(np_t))).to(cuda_device)
+    d1 = torch.from_numpy(np.ascontiguousarray(I1.astype(np_t))).to(cuda_device)
+    alg = ocb.SparsePyrLKOpticalFlow_create()
+    nxt, status, err = alg.calc(d0, d1, torch.from_numpy(pts).to(cuda_device).reshape(1, -1, 2), wantErr=True)
+    torch.cuda.synchronize()
+    nxt, status, err = nxt.cpu().numpy().reshape(-1, 2), status.cpu().numpy(), err.cpu().numpy()
+    ratio = _mismatch(nxt, status, gold, st_gold)
+    assert ratio <= 0.01, ratio
+    ok = (status != 0) & (st_gold != 0)
+    g = gt[np.clip(pts[:, 1].astype(int), 0, 299), np.clip(pts[:, 0].astype(int), 0, 399)]
+    assert np.median(np.linalg.norm((nxt - pts) - g, axis=1)[ok]) < 0.1
+    assert np.isfinite(err[ok]).all() and (err[ok] >= 0).all()
+
+
+def test_sparse_pyrlk_rejects_unsupported_types(cuda_device):
+    import torch
+    import opencv_contrib_b200 as ocb
+    alg = ocb.SparsePyrLKOpticalFlow_create()
+    pts = torch.tensor([[20.0, 20.0]], device=cuda_device)
+    a = torch.zeros((64, 64, 2), dtype=torch.uint8, device=cuda_device)      # 2 channels: funcs[][1] == 0 (pyrlk.cpp:197)
+    with pytest.raises(ocb.B2FError):
+        alg.calc(a, a, pts)
+    b = torch.zeros((64, 64), dtype=torch.int16, device=cuda_device)         # CV_16S is not instantiated
+    with pytest.raises(ocb.B2FError):
+        alg.calc(b, b, pts)
