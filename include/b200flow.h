@@ -161,11 +161,11 @@ typedef enum b2f_param_id {
     /* engine knobs (no reference counterpart) */
     B2F_ENGINE_FUSED_ITERS = 900, /* TV-L1: inner iterations fused per HBM pass (0 = auto)     */
     B2F_ENGINE_USE_GRAPH = 901,   /* capture the fixed schedule in a CUDA graph (default 1)    */
-    B2F_ENGINE_KERNEL_PATH = 902, /* TV-L1: 0 = auto (packed-FP32 persistent TMA kernel), 1 = unfused
-                                     reference-shaped kernels, 2 = blocked kernel without TMA,
-                                     4 = scalar persistent TMA kernel (3: without elect.sync)   */
-    B2F_ENGINE_AUX_PATH = 903     /* TV-L1: 0 = separable warp kernel, 1 = tap-by-tap warp kernel
-                                     (accumulation in the reference's order)                     */
+    B2F_ENGINE_KERNEL_PATH = 902, /* TV-L1: 0 = auto (persistent TMA kernel), 1 = unfused reference-shaped
+                                     kernels, 2 = blocked kernel without TMA, 3 = TMA kernel without
+                                     elect.sync, 5 = packed-FP32 (f32x2) TMA kernel, 6 = 2x2-cluster kernel */
+    B2F_ENGINE_AUX_PATH = 903     /* TV-L1: 0 = tap-by-tap warp kernel (accumulation in the reference's
+                                     order), 1 = separable warp kernel                           */
 } b2f_param_id;
 
 /* cv::medianBlur for CV_32FC1, ksize 3 or 5, replicated border, not in place: the primitive behind
@@ -277,6 +277,30 @@ B2F_API int b2f_batch_run_device(b2f_batch *b, int n_pairs, const b2f_image *I0,
 /* n_pairs HOST pairs -> host flows: one worker thread per stream runs b2f_calc_host on its share, so the copies
  * of one pair overlap the solves of the others.  Returns when every flow has landed. */
 B2F_API int b2f_batch_run_host(b2f_batch *b, int n_pairs, const b2f_image *I0, const b2f_image *I1, b2f_image *flow);
+/* ---- multi-GPU: one process per GPU, pairs sharded by the caller (rank r owns a contiguous block), NO data-path
+ *      collective; the only exchange is the gather of the finished flows to rank `dst`, done here over NCCL
+ *      (ncclSend / ncclRecv; libnccl.so.2 is taken from the process or dlopen'ed -- never a link dependency).
+ *      Every flow is sent as soon as its own solve has finished, on a communication stream, so transfers overlap
+ *      the remaining solves.  Replaces what callers of the reference do by hand after looping over calc().
+ *        b2f_comm_unique_id   rank 0 creates the 128-byte NCCL id, the caller distributes it (any side channel)
+ *        b2f_comm_create      collective over all ranks; binds to the CURRENT device; nranks == 1 needs no NCCL
+ *        b2f_comm_adopt       wrap an ncclComm_t the application already owns (not destroyed by b2f_comm_destroy)
+ *        b2f_batch_run_device_gather   like b2f_batch_run_device, plus the gather: on rank `dst`, gathered[r * n_pairs + i]
+ *                             receives pair i of rank r (contiguous CV_32FC2, step == cols * 8; the entry for r == dst may
+ *                             alias flow[i]); other ranks pass NULL.  Same n_pairs and sizes on every rank.
+ *      Everything is ordered on `cuda_stream` like b2f_batch_run_device: no host synchronisation. ---- */
+typedef struct b2f_comm b2f_comm;
+B2F_API int b2f_comm_available(void);
+B2F_API int b2f_comm_unique_id(void *id128, size_t bytes);
+B2F_API int b2f_comm_create(const void *id128, size_t bytes, int rank, int nranks, b2f_comm **out);
+B2F_API int b2f_comm_adopt(void *nccl_comm, b2f_comm **out);
+B2F_API int b2f_comm_rank(const b2f_comm *c);
+B2F_API int b2f_comm_nranks(const b2f_comm *c);
+B2F_API int b2f_comm_last_nccl_error(const b2f_comm *c);
+B2F_API void b2f_comm_destroy(b2f_comm *c);
+B2F_API int b2f_batch_run_device_gather(b2f_batch *b, int n_pairs, const b2f_image *I0, const b2f_image *I1,
+                                        b2f_image *flow, b2f_comm *comm, int dst, b2f_image *gathered, void *cuda_stream);
+
 B2F_API uint64_t b2f_batch_launches(b2f_batch *b);
 B2F_API int b2f_batch_reset_stats(b2f_batch *b);
 B2F_API void b2f_batch_destroy(b2f_batch *b);

@@ -8,8 +8,8 @@
 //     events only, so CUDA events on that stream bracket the whole batch and nothing blocks the host;
 //   * run_host: one worker thread per stream uploads, solves and downloads its share through b2f_calc_host, so
 //     the copies of one pair overlap the solves of the others; returns when every flow is in host memory.
-// Sharding across GPUs / processes (rank r owns a contiguous block of pairs, NCCL result gather) stays with the
-// caller's process framework (opencv_contrib_b200/batch.py over torch.distributed).
+// Sharding across GPUs is one process per GPU (rank r owns a contiguous block of pairs); the result gather to one rank
+// is native too: b2f_batch_run_device_gather sends every flow over NCCL as soon as its solve finishes (comm.cu).
 #include <atomic>
 #include <new>
 #include <thread>
@@ -25,6 +25,50 @@ struct b2f_batch {
     cudaEvent_t start = nullptr;
     int last_status = B2F_OK;
 };
+
+struct b2f_comm;
+namespace b2f {
+// comm.cu
+int comm_enqueue_pair(b2f_comm *c, int i, int n_pairs, cudaStream_t es, const b2f_image *flow_i, int dst, b2f_image *gathered);
+int comm_fork(b2f_comm *c, cudaEvent_t start);
+int comm_join(b2f_comm *c, cudaStream_t cur);
+int comm_device(const b2f_comm *c);
+
+int batch_run_device_impl(b2f_batch *b, int n_pairs, const b2f_image *I0, const b2f_image *I1, b2f_image *flow,
+                          cudaStream_t cur, b2f_comm *comm, int dst, b2f_image *gathered) {
+    if (!b || n_pairs < 0 || (n_pairs > 0 && (!I0 || !I1 || !flow))) return B2F_BAD_ARG;
+    if (n_pairs == 0) return B2F_OK;
+    if (comm && comm_device(comm) != b->device) return B2F_BAD_ARG;
+    DeviceScope dev(b->device);
+    const int ns = static_cast<int>(b->streams.size());
+    const int used = n_pairs < ns ? n_pairs : ns;
+    auto fail = [&]() {
+        cudaGetLastError();
+        return B2F_CUDA_ERROR;
+    };
+    if (cudaEventRecord(b->start, cur) != cudaSuccess) return fail();
+    for (int k = 0; k < used; ++k)
+        if (cudaStreamWaitEvent(b->streams[k], b->start, 0) != cudaSuccess) return fail();
+    int status = comm ? comm_fork(comm, b->start) : B2F_OK;
+    for (int i = 0; i < n_pairs && status == B2F_OK; ++i) {
+        const int k = i % ns;
+        status = b2f_calc(b->engines[k], &I0[i], &I1[i], &flow[i], b->streams[k]);
+        if (status == B2F_OK && comm) status = comm_enqueue_pair(comm, i, n_pairs, b->streams[k], &flow[i], dst, gathered);
+    }
+    // join even after a failure so the caller's stream stays ordered behind whatever was enqueued
+    for (int k = 0; k < used; ++k) {
+        if (cudaEventRecord(b->done[k], b->streams[k]) != cudaSuccess) return fail();
+        if (cudaStreamWaitEvent(cur, b->done[k], 0) != cudaSuccess) return fail();
+    }
+    if (comm) {
+        const int js = comm_join(comm, cur);
+        if (status == B2F_OK) status = js;
+    }
+    if (status == B2F_OK && cur == nullptr && cudaDeviceSynchronize() != cudaSuccess) return fail();
+    b->last_status = status;
+    return status;
+}
+}  // namespace b2f
 
 extern "C" {
 
@@ -105,32 +149,7 @@ int b2f_batch_set_param(b2f_batch *b, int id, double value) {
 
 int b2f_batch_run_device(b2f_batch *b, int n_pairs, const b2f_image *I0, const b2f_image *I1, b2f_image *flow,
                          void *cuda_stream) {
-    if (!b || n_pairs < 0 || (n_pairs > 0 && (!I0 || !I1 || !flow))) return B2F_BAD_ARG;
-    if (n_pairs == 0) return B2F_OK;
-    b2f::DeviceScope dev(b->device);
-    cudaStream_t cur = static_cast<cudaStream_t>(cuda_stream);
-    const int ns = static_cast<int>(b->streams.size());
-    const int used = n_pairs < ns ? n_pairs : ns;
-    auto fail = [&]() {
-        cudaGetLastError();
-        return B2F_CUDA_ERROR;
-    };
-    if (cudaEventRecord(b->start, cur) != cudaSuccess) return fail();
-    for (int k = 0; k < used; ++k)
-        if (cudaStreamWaitEvent(b->streams[k], b->start, 0) != cudaSuccess) return fail();
-    int status = B2F_OK;
-    for (int i = 0; i < n_pairs && status == B2F_OK; ++i) {
-        const int k = i % ns;
-        status = b2f_calc(b->engines[k], &I0[i], &I1[i], &flow[i], b->streams[k]);
-    }
-    // join even after a failure so the caller's stream stays ordered behind whatever was enqueued
-    for (int k = 0; k < used; ++k) {
-        if (cudaEventRecord(b->done[k], b->streams[k]) != cudaSuccess) return fail();
-        if (cudaStreamWaitEvent(cur, b->done[k], 0) != cudaSuccess) return fail();
-    }
-    if (status == B2F_OK && cur == nullptr && cudaDeviceSynchronize() != cudaSuccess) return fail();
-    b->last_status = status;
-    return status;
+    return b2f::batch_run_device_impl(b, n_pairs, I0, I1, flow, static_cast<cudaStream_t>(cuda_stream), nullptr, 0, nullptr);
 }
 
 int b2f_batch_run_host(b2f_batch *b, int n_pairs, const b2f_image *I0, const b2f_image *I1, b2f_image *flow) {

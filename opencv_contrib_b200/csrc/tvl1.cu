@@ -127,11 +127,13 @@ __device__ __forceinline__ void keys_weights(float t, float (&k)[4]) {
     k[3] = (0.5f * t - 0.5f) * t * t;
 }
 
-// Separable form of the same warp (round 2, the default): w_ij = kx[i] * ky[j], so the three weighted sums are row
+// Separable form of the same warp (round 2, opt-in as aux_path 1): w_ij = kx[i] * ky[j], so the three weighted sums are row
 // sums r[j] = sum_i kx[i] W[j][i+1] (6 rows), rx[j] = sum_i kx[i] (W[j][i+2] - W[j][i]) (4 rows) combined with ky:
 //   I1w = sum_j ky[j] r[j+1],  I1wx = 0.5 sum_j ky[j] rx[j+1],  I1wy = 0.5 sum_j ky[j] (r[j+2] - r[j]),
-// about half the arithmetic of the tap-by-tap form (which stays available as aux_path 1 and for the few pixels whose
-// window touches the image border).  Results differ from the tap-by-tap accumulation by rounding only.
+// about half the arithmetic of the tap-by-tap form (which handles the few pixels whose window touches the image border).
+// Results differ from the tap-by-tap accumulation by rounding only.  Measured on B200 (1080p 5x10x30): 1.24 ms per
+// pair against 1.26 ms -- the kernel is bound by its 36-texel gather, not by arithmetic -- so the reference-ordered
+// kernel stays the default.
 __global__ void __launch_bounds__(256) k_tvl1_warp_sep(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
                                                        Plane grad, Plane rho, int rows, int cols) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -595,9 +597,9 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
         int done = 0;
         while (done < count) {
             const int kk = tvl1_blocked_pick_k(knobs.fused_iters, count - done, rows, cols);
-            if (use_tma && (knobs.kernel_path == 0 || knobs.kernel_path == 5))
+            if (use_tma && knobs.kernel_path == 5)  // packed-FP32 variant: measured 8 % slower than the scalar kernel
                 tvl1_packed_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
-            else if (use_tma)  // kernel_path 4: the round-1 scalar TMA kernel (3: without elect.sync)
+            else if (use_tma)  // 0 / 4: the scalar persistent TMA kernel (3: without elect.sync)
                 tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path != 3);
             else
                 tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);
@@ -624,12 +626,12 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
 
     for (int w = 0; w < P.warps; ++w) {
         point_T_at(cur);
-        if (knobs.aux_path == 1)  // tap-by-tap accumulation in the reference's order
-            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy,
-                       T.grad, T.rho_c, rows, cols);
-        else
+        if (knobs.aux_path == 1)  // separable form: half the arithmetic, measured no faster (the kernel is gather-bound)
             B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_sep, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx,
                        T.I1wy, T.grad, T.rho_c, rows, cols);
+        else  // tap-by-tap accumulation in the reference's order
+            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy,
+                       T.grad, T.rho_c, rows, cols);
 
         if (blocked_ok && !(P.epsilon > 0.0)) {  // fixed schedule
             if (med_k == 1) {

@@ -18,10 +18,11 @@ from oracle import synth, metrics, tvl1_cpu, tvl1_gpu_model as gm
 pytestmark = pytest.mark.gpu
 
 
-def _run(dev, I0, I1, path=0, fused=0, graph=1, stream=None, init=None, _median=None, **kw):
+def _run(dev, I0, I1, path=0, fused=0, graph=1, stream=None, init=None, _median=None, aux=0, **kw):
     import torch
     import opencv_contrib_b200 as ocb
     alg = ocb.OpticalFlowDual_TVL1_create(**kw)
+    alg.setEngineOption("aux_path", aux)
     if _median is not None:
         alg.setMedianFiltering(_median[0])
         alg.setMedianPeriod(_median[1])
@@ -45,6 +46,9 @@ def test_engine_matches_cuda_semantics_model(cuda_device, h, w, kind, seed):
         st = metrics.epe_stats(got, ref)
         assert np.isfinite(got).all() and st["max"] <= 1e-3, (path, st)
     assert alg.getStats()["launches"] > 0
+    sep, _ = _run(cuda_device, I0, I1, aux=1, **kw)       # separable warp kernel: same values up to rounding
+    st = metrics.epe_stats(sep, ref)
+    assert np.isfinite(sep).all() and st["max"] <= 1e-3, ("separable warp", st)
 
 
 @pytest.mark.parametrize("K", [1, 2, 3, 5, 6, 7, 10, 12])
@@ -53,8 +57,8 @@ def test_blocked_kernel_bit_identical_to_unfused(cuda_device, K):
     I0, I1, _ = synth.make_pair(203, 277, seed=3, kind="smooth")
     kw = dict(nscales=3, warps=2, epsilon=0.0, iterations=23)
     a, _ = _run(cuda_device, I0, I1, path=1, **kw)
-    # 0 = packed-FP32 (f32x2) persistent TMA kernel, 4 = scalar persistent TMA kernel, 2 = blocked kernel, plain loads
-    for path in (0, 4, 2):
+    # 0 = scalar persistent TMA kernel, 5 = packed-FP32 (f32x2) variant, 2 = blocked kernel with plain loads
+    for path in (0, 5, 2):
         for graph in (0, 1):
             b, _ = _run(cuda_device, I0, I1, path=path, fused=K, graph=graph, **kw)
             assert np.array_equal(a, b), (path, K, graph, float(np.abs(a - b).max()))

@@ -9,7 +9,7 @@ dev = torch.device("cuda:0")
 I0, I1, gt = synth.make_pair(1080, 1920, seed=0, kind="smooth")
 d0, d1 = torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev)
 ref = None
-cases = [(int(a), int(b)) for a, b in (c.split(":") for c in (sys.argv[1:] or ["4:8", "0:8", "0:10", "0:12", "0:6", "0:4"]))]
+cases = [(int(a), int(b)) for a, b in (c.split(":") for c in (sys.argv[1:] or ["0:8", "5:8", "6:8"]))]
 for path, K in cases:
     algs = [ocb.OpticalFlowDual_TVL1_create(nscales=5, warps=10, epsilon=0.0, iterations=30) for _ in range(4)]
     for a in algs:
