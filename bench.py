@@ -424,14 +424,18 @@ def measure(workload: str, args, rank: int, world: int, dev, steps: int, sampler
     flow_views = [flows[i] for i in range(B)]
     # native batch front end (csrc/batch.cu): N engine handles on N streams, one C call per batch
     batcher = NativeFlowBatch(spec["family"], spec["params"], n_streams=streams)
+    comm = NATIVE_COMM.get("comm") if (world > 1 and args.gather == "native") else None
     gathered = None
-    if world > 1 and rank == 0:
-        gathered = [torch.empty_like(flows) for _ in range(world)]
+    if world > 1 and rank == 0:  # native: rank 0's own flows are computed straight into their slot
+        gathered = [flows if (r == 0 and comm is not None) else torch.empty_like(flows) for r in range(world)]
 
     def step():
-        batcher.run_device(pairs, flow_views)
-        if world > 1:
-            gather_flows(flows, dst=0, out=gathered)
+        if comm is not None:   # per-pair ncclSend / ncclRecv on the library's communication stream, overlapped with the solves
+            batcher.run_device_gather(pairs, flow_views, comm, 0, gathered)
+        else:
+            batcher.run_device(pairs, flow_views)
+            if world > 1:      # one torch.distributed.gather after the whole batch
+                gather_flows(flows, dst=0, out=gathered)
 
     def barrier():
         if world > 1:
@@ -462,7 +466,9 @@ def measure(workload: str, args, rank: int, world: int, dev, steps: int, sampler
            "warmup": args.warmup, "ms_per_step": total_ms / steps, "gpu_launches": int(launches),
            "config": {"workload": spec["name"], "pairs_per_step_per_gpu": B, "streams_per_gpu": streams,
                       "parallelism": "pairs sharded over %d rank(s)%s" % (
-                          world, ", NCCL gather of flows to rank 0 inside the step" if world > 1 else ""),
+                          world, (", NCCL gather of flows to rank 0 inside the step (%s)" % (
+                              "native: per-pair ncclSend/ncclRecv overlapped with the solves" if comm is not None
+                              else "torch.distributed.gather after the batch")) if world > 1 else ""),
                       "l2": "inputs per step (%.0f MB u8) exceed the 126 MB L2; engine working set ~%.1f GB/pair" % (
                           B * 2 * H * W / 1e6, 0.3 * H * W / (1080 * 1920))}}
     if clocks is not None:
@@ -494,6 +500,9 @@ def measure(workload: str, args, rank: int, world: int, dev, steps: int, sampler
     return rec, pairs, flow_views
 
 
+NATIVE_COMM = {}
+
+
 def nccl_init_lines(world: int):
     """Communicator lines of this run's NCCL INFO logs (rank 0's view of `nranks`)."""
     out = []
@@ -515,6 +524,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if args.gather == "native":
+            from opencv_contrib_b200.batch import NativeComm
+            NATIVE_COMM["comm"] = NativeComm.from_torch_distributed()
 
     head = args.workload or "tvl1"
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -566,6 +578,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             for ln in lines:
                 print(ln, file=sys.stderr, flush=True)
         print(json.dumps(line), flush=True)
+    NATIVE_COMM.clear()
     if world > 1:
         dist.destroy_process_group()
 
@@ -583,6 +596,9 @@ def main():
     ap.add_argument("--streams", type=int, default=0,
                     help="engine instances / CUDA streams per GPU (0 = per workload: 4 for tvl1, whose persistent kernels "
                          "fill the GPU on their own; 8 for farneback, whose coarse levels are launch-bound)")
+    ap.add_argument("--gather", default="native", choices=["native", "torch"],
+                    help="N > 1: result gather through libb200flow's own NCCL communicator (per pair, overlapped) or one "
+                         "torch.distributed.gather per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary single-stream measurements")
     args = ap.parse_args()

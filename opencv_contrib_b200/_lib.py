@@ -117,6 +117,15 @@ SYMBOLS = [
     ("b2f_batch_set_param", C.c_int, [_H, C.c_int, C.c_double]),
     ("b2f_batch_run_device", C.c_int, [_H, C.c_int, _IMG, _IMG, _IMG, C.c_void_p]),
     ("b2f_batch_run_host", C.c_int, [_H, C.c_int, _IMG, _IMG, _IMG]),
+    ("b2f_batch_run_device_gather", C.c_int, [_H, C.c_int, _IMG, _IMG, _IMG, _H, C.c_int, _IMG, C.c_void_p]),
+    ("b2f_comm_available", C.c_int, []),
+    ("b2f_comm_unique_id", C.c_int, [C.c_void_p, C.c_size_t]),
+    ("b2f_comm_create", C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(_H)]),
+    ("b2f_comm_adopt", C.c_int, [C.c_void_p, C.POINTER(_H)]),
+    ("b2f_comm_rank", C.c_int, [_H]),
+    ("b2f_comm_nranks", C.c_int, [_H]),
+    ("b2f_comm_last_nccl_error", C.c_int, [_H]),
+    ("b2f_comm_destroy", None, [_H]),
     ("b2f_batch_launches", C.c_uint64, [_H]),
     ("b2f_batch_reset_stats", C.c_int, [_H]),
     ("b2f_batch_destroy", None, [_H]),

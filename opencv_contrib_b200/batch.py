@@ -155,11 +155,82 @@ class NativeFlowBatch:
         if st != 0:
             raise self._libmod.B2FError(st)
 
+    def run_device_gather(self, pairs, flows, comm: "NativeComm", dst: int = 0, gathered=None, stream=None) -> None:
+        """run_device + the native result gather (b2f_batch_run_device_gather): every flow goes to rank ``dst`` over NCCL
+        as soon as its own solve has finished, on the library's communication stream.  ``gathered``: on ``dst`` a list of
+        ``nranks`` stacked tensors (n, H, W, 2) (index = source rank; the entry for ``dst`` may be the tensor the
+        ``flows`` views come from), None elsewhere.  Ordered on ``stream`` like run_device; nothing blocks the host."""
+        import torch
+        from .cudaoptflow import _image_from_tensor
+        n, a, b, f = self._arrays(pairs, flows, _image_from_tensor)
+        g = None
+        if comm.rank == dst:
+            if gathered is None or len(gathered) != comm.nranks:
+                raise ValueError("rank dst needs one receive tensor per rank")
+            g = (self._libmod.b2f_image * (n * comm.nranks))()
+            for r, t in enumerate(gathered):
+                for i in range(n):
+                    g[r * n + i] = _image_from_tensor(t[i], True)
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        st = self._lib.b2f_batch_run_device_gather(self._b, n, a, b, f, comm._c, dst, g,
+                                                   self._C.c_void_p(stream.cuda_stream))
+        if st != 0:
+            raise self._libmod.B2FError(st)
+
     def launches(self) -> int:
         return int(self._lib.b2f_batch_launches(self._b))
 
     def reset_stats(self) -> None:
         self._lib.b2f_batch_reset_stats(self._b)
+
+
+class NativeComm:
+    """NCCL communicator owned by libb200flow.so (csrc/comm.cu) for the per-pair result gather of
+    ``NativeFlowBatch.run_device_gather``.  One per process / GPU; creation is collective.
+
+        comm = NativeComm.from_torch_distributed()      # id made on rank 0, broadcast through the process group
+    """
+
+    def __init__(self, unique_id: bytes, rank: int, nranks: int):
+        import ctypes as C
+        from . import _lib
+        self._C, self._libmod, self._lib = C, _lib, _lib.lib()
+        self._c = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128) if nranks > 1 else None
+        st = self._lib.b2f_comm_create(buf, 128, rank, nranks, C.byref(self._c))
+        if st != 0:
+            self._c = None
+            raise _lib.B2FError(st)
+        self.rank, self.nranks = rank, nranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _lib
+        buf = C.create_string_buffer(128)
+        st = _lib.lib().b2f_comm_unique_id(buf, 128)
+        if st != 0:
+            raise _lib.B2FError(st)
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, group=None):
+        """Bootstrap over an initialised torch.distributed process group (any backend): rank 0 creates the NCCL id
+        and broadcasts its 128 bytes; every rank then joins on its CURRENT CUDA device."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 and world > 1 else b""]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        return cls(box[0], rank, world)
+
+    def close(self):
+        c, self._c = getattr(self, "_c", None), None
+        if c:
+            self._lib.b2f_comm_destroy(c)
+
+    __del__ = close
 
 
 def gather_flows(local_flows, dst: int = 0, group=None, out=None):
