@@ -609,6 +609,351 @@ __global__ void __launch_bounds__(NT, 1)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Thread-block-cluster variant (round 2, kernel_path 6 / 7): CX x CY CTAs of one cluster work on ONE super-region of
+// (64 CX) x (64 CY) pixels and exchange the one-pixel boundary of every half iteration through distributed shared
+// memory, so only the OUTER border of the super-region is halo: with K = 8 a 2 x 2 cluster keeps 112^2 of 128^2
+// computed pixels (76.6 %) where a lone CTA keeps 48^2 of 64^2 (56.3 %).
+//
+// Per CTA everything is as in k_tvl1_blocked_tma (64x64 region, 4x2 register micro-tiles, TMA-prefetched staging).
+// On top of it, per half iteration and per neighbouring CTA inside the cluster:
+//   after the dual update   my last column of (p11, p21) -> right neighbour's left ghost column,
+//                           my last row    of (p12, p22) -> lower neighbour's upper ghost row;
+//   after the primal update my first column of (u1, u2)  -> left neighbour's right ghost column,
+//                           my first row    of (u1, u2)  -> upper neighbour's lower ghost row.
+// Values travel as st.async (one 4-byte remote store each) that complete_tx on an mbarrier in the RECEIVING CTA; the
+// receiver arms that barrier with the byte count it expects and waits on it (acquire.cluster) at the start of the
+// half iteration that consumes the ghosts.  No cluster-wide barrier inside the loop: a CTA only ever waits for the
+// neighbours it reads from.  Measured one-way latency of such a hand-off on B200: 216 cycles
+// (tools/ubench/ubench_fp32x2_dsmem.cu); to keep it off the critical path every half iteration computes the five pixels
+// of each micro-tile that need ghosts and produce the values to send FIRST, sends, and then computes the other three.
+// Overwrite safety needs no extra synchronisation: a neighbour can only produce the next value for a ghost cell after
+// it received what this CTA computed FROM the current one (the two hand-offs of an iteration depend on each other).
+// ---------------------------------------------------------------------------------------------
+struct ClusterGhosts {                 // 64 floats each, index = region row (columns) or region column (rows)
+    float p11L[R], p21L[R];            // left ghost column, read by the primal update of lx == 0
+    float p12U[R], p22U[R];            // upper ghost row,   read by the primal update of tr == 0
+    float u1R[R], u2R[R];              // right ghost column, read by the dual update of lx == 15
+    float u1D[R], u2D[R];              // lower ghost row,    read by the dual update of tr == 31
+};
+
+__device__ __forceinline__ uint32_t cluster_map(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "DONE_C:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct ClusterLinks {   // remote addresses (shared::cluster window) of the neighbours' ghost arrays and barriers; 0 = no neighbour
+    uint32_t right_p11L, right_p21L, right_barP;   // right neighbour: its left ghost column
+    uint32_t down_p12U, down_p22U, down_barP;      // lower neighbour: its upper ghost row
+    uint32_t left_u1R, left_u2R, left_barU;        // left neighbour: its right ghost column
+    uint32_t up_u1D, up_u2D, up_barU;              // upper neighbour: its lower ghost row
+    bool has_left, has_right, has_up, has_down;
+};
+
+// K iterations with ghost exchange.  Same arithmetic, same operand order per pixel as tile_iterate.
+template <bool BORDER>
+__device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, ClusterGhosts *gh, const ClusterLinks &L,
+                                                     uint64_t *barP, uint64_t *barU, uint32_t &parP, uint32_t &parU,
+                                                     int iters, const Tvl1Scalars k, int lx, int tr, int gxb, int gyb, int W,
+                                                     int H) {
+    float *ex_u1 = ex, *ex_u2 = ex + EX_F, *ex_p12 = ex + 2 * EX_F, *ex_p22 = ex + 3 * EX_F;
+    const int mine = tr * R + 4 * lx;
+    const int up = max(tr - 1, 0) * R + 4 * lx;
+    const int dn = min(tr + 1, 31) * R + 4 * lx;
+    const bool wait_p = L.has_left || L.has_up, wait_u = L.has_right || L.has_down;
+    const uint32_t bytes_p = (L.has_left ? 2u * R * 4u : 0u) + (L.has_up ? 2u * R * 4u : 0u);
+    const uint32_t bytes_u = (L.has_right ? 2u * R * 4u : 0u) + (L.has_down ? 2u * R * 4u : 0u);
+
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
+
+    auto send_p = [&]() {  // my last column / last row of the dual variables -> right / lower neighbour
+        if (L.has_right && lx == 15) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                st_async_f32(L.right_p11L + 4u * (2 * tr + j), r.p11[j][3], L.right_barP);
+                st_async_f32(L.right_p21L + 4u * (2 * tr + j), r.p21[j][3], L.right_barP);
+            }
+        }
+        if (L.has_down && tr == 31) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                st_async_f32(L.down_p12U + 4u * (4 * lx + i), r.p12[1][i], L.down_barP);
+                st_async_f32(L.down_p22U + 4u * (4 * lx + i), r.p22[1][i], L.down_barP);
+            }
+        }
+    };
+    auto send_u = [&]() {  // my first column / first row of the flow -> left / upper neighbour
+        if (L.has_left && lx == 0) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                st_async_f32(L.left_u1R + 4u * (2 * tr + j), r.u1[j][0], L.left_barU);
+                st_async_f32(L.left_u2R + 4u * (2 * tr + j), r.u2[j][0], L.left_barU);
+            }
+        }
+        if (L.has_up && tr == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                st_async_f32(L.up_u1D + 4u * (4 * lx + i), r.u1[0][i], L.up_barU);
+                st_async_f32(L.up_u2D + 4u * (4 * lx + i), r.u2[0][i], L.up_barU);
+            }
+        }
+    };
+
+    st4(ex_p12 + mine, r.p12[1]);
+    st4(ex_p22 + mine, r.p22[1]);
+    send_p();
+    __syncthreads();
+
+    for (int it = 0; it < iters; ++it) {
+        // ---------------- primal update (estimateU) ----------------
+        {
+            float up12[4], up22[4], l11[2], l21[2];
+            ld4(ex_p12 + up, up12);
+            ld4(ex_p22 + up, up22);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                l11[j] = __shfl_up_sync(0xffffffffu, r.p11[j][3], 1, 16);
+                l21[j] = __shfl_up_sync(0xffffffffu, r.p21[j][3], 1, 16);
+            }
+            if (wait_p) {
+                mbar_wait_cluster(barP, parP);
+                parP ^= 1;
+                if (L.has_left && lx == 0) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { l11[j] = gh->p11L[2 * tr + j]; l21[j] = gh->p21L[2 * tr + j]; }
+                }
+                if (L.has_up && tr == 0) {
+                    ld4(gh->p12U + 4 * lx, up12);
+                    ld4(gh->p22U + 4 * lx, up22);
+                }
+            }
+            auto px = [&](int j, int i) {
+                float pl11 = i ? r.p11[j][i ? i - 1 : 0] : l11[j];
+                float pl21 = i ? r.p21[j][i ? i - 1 : 0] : l21[j];
+                float pu12 = j ? r.p12[0][i] : up12[i];
+                float pu22 = j ? r.p22[0][i] : up22[i];
+                if (BORDER) {
+                    if (gxb + i == 0) { pl11 = 0.f; pl21 = 0.f; }
+                    if (gyb + j == 0) { pu12 = 0.f; pu22 = 0.f; }
+                }
+                float a, b;
+                tvl1_update_u(k, r.Ix[j][i], r.Iy[j][i], r.gr[j][i], r.rc[j][i], r.u1[j][i], r.u2[j][i], r.p11[j][i], pl11,
+                              r.p12[j][i], pu12, r.p21[j][i], pl21, r.p22[j][i], pu22, a, b);
+                r.u1[j][i] = a;
+                r.u2[j][i] = b;
+            };
+            // first the five pixels that read ghosts / feed the neighbours (row 0 and column 0), then the hand-off
+            px(0, 0); px(0, 1); px(0, 2); px(0, 3); px(1, 0);
+            send_u();
+            px(1, 1); px(1, 2); px(1, 3);
+        }
+        st4(ex_u1 + mine, r.u1[0]);
+        st4(ex_u2 + mine, r.u2[0]);
+        __syncthreads();
+        if (wait_p && threadIdx.x == 0) mbar_expect_tx(barP, bytes_p);  // every thread is past this phase's wait: re-arm
+
+        // ---------------- dual update (estimateDualVariables) ----------------
+        {
+            float dn1[4], dn2[4], r1[2], r2[2];
+            ld4(ex_u1 + dn, dn1);
+            ld4(ex_u2 + dn, dn2);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                r1[j] = __shfl_down_sync(0xffffffffu, r.u1[j][0], 1, 16);
+                r2[j] = __shfl_down_sync(0xffffffffu, r.u2[j][0], 1, 16);
+            }
+            if (wait_u) {
+                mbar_wait_cluster(barU, parU);
+                parU ^= 1;
+                if (L.has_right && lx == 15) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { r1[j] = gh->u1R[2 * tr + j]; r2[j] = gh->u2R[2 * tr + j]; }
+                }
+                if (L.has_down && tr == 31) {
+                    ld4(gh->u1D + 4 * lx, dn1);
+                    ld4(gh->u2D + 4 * lx, dn2);
+                }
+            }
+            auto px = [&](int j, int i) {
+                const float c1 = r.u1[j][i], c2 = r.u2[j][i];
+                const float ur1 = i < 3 ? r.u1[j][i < 3 ? i + 1 : 3] : r1[j];
+                const float ur2 = i < 3 ? r.u2[j][i < 3 ? i + 1 : 3] : r2[j];
+                const float ud1 = j == 0 ? r.u1[1][i] : dn1[i];
+                const float ud2 = j == 0 ? r.u2[1][i] : dn2[i];
+                float ux1 = __fsub_rn(ur1, c1), uy1 = __fsub_rn(ud1, c1);
+                float ux2 = __fsub_rn(ur2, c2), uy2 = __fsub_rn(ud2, c2);
+                if (BORDER) {
+                    if (gxb + i == W - 1) { ux1 = 0.f; ux2 = 0.f; }
+                    if (gyb + j == H - 1) { uy1 = 0.f; uy2 = 0.f; }
+                }
+                tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, r.p11[j][i], r.p12[j][i], r.p21[j][i], r.p22[j][i]);
+            };
+            // first row 1 and column 3 (they read ghosts and produce what the neighbours wait for), then the hand-off
+            px(1, 0); px(1, 1); px(1, 2); px(1, 3); px(0, 3);
+            if (it + 1 < iters) send_p();   // the last dual update of a tile has no consumer: the next tile publishes afresh
+            px(0, 0); px(0, 1); px(0, 2);
+        }
+        st4(ex_p12 + mine, r.p12[1]);
+        st4(ex_p22 + mine, r.p22[1]);
+        __syncthreads();
+        if (wait_u && threadIdx.x == 0) mbar_expect_tx(barU, bytes_u);
+    }
+}
+
+// cluster_x * cluster_y CTAs per cluster (rank = qy * cluster_x + qx); grid = clusters * cluster size, persistent over
+// super-tiles.  All CTAs of a cluster walk the same super-tile sequence (also the ones whose quadrant lies outside the
+// image: zero-filled by TMA, nothing stored), so the hand-off protocol is uniform.
+__global__ void __launch_bounds__(NT, 1)
+    k_tvl1_cluster_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12, Plane o_p21,
+                       Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int cluster_x, int cluster_y,
+                       int stile_x, int stile_y, int stiles_x, int n_super) {
+    extern __shared__ __align__(1024) float smem[];
+    float *stage = smem;
+    float *ex = smem + N_IN * PLANE_F;
+    ClusterGhosts *gh = reinterpret_cast<ClusterGhosts *>(ex + 4 * EX_F);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(gh + 1);  // [0] TMA staging, [1] ghosts of the primal update, [2] of the dual
+    uint64_t *barP = bar + 1, *barU = bar + 2;
+
+    const int tid = threadIdx.x;
+    const int lx = tid & 15, tr = tid >> 4;
+    constexpr uint32_t kStageBytes = N_IN * PLANE_F * sizeof(float);
+    const int csize = cluster_x * cluster_y;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int qx = (int)rank % cluster_x, qy = (int)rank / cluster_x;
+    const int cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
+
+    ClusterLinks L;
+    L.has_left = qx > 0; L.has_right = qx < cluster_x - 1; L.has_up = qy > 0; L.has_down = qy < cluster_y - 1;
+    {
+        const uint32_t rr = L.has_right ? rank + 1 : rank, rd = L.has_down ? rank + cluster_x : rank;
+        const uint32_t rl = L.has_left ? rank - 1 : rank, ru = L.has_up ? rank - cluster_x : rank;
+        L.right_p11L = cluster_map(smem_u32(gh->p11L), rr); L.right_p21L = cluster_map(smem_u32(gh->p21L), rr);
+        L.right_barP = cluster_map(smem_u32(barP), rr);
+        L.down_p12U = cluster_map(smem_u32(gh->p12U), rd); L.down_p22U = cluster_map(smem_u32(gh->p22U), rd);
+        L.down_barP = cluster_map(smem_u32(barP), rd);
+        L.left_u1R = cluster_map(smem_u32(gh->u1R), rl); L.left_u2R = cluster_map(smem_u32(gh->u2R), rl);
+        L.left_barU = cluster_map(smem_u32(barU), rl);
+        L.up_u1D = cluster_map(smem_u32(gh->u1D), ru); L.up_u2D = cluster_map(smem_u32(gh->u2D), ru);
+        L.up_barU = cluster_map(smem_u32(barU), ru);
+    }
+    const uint32_t bytes_p = (L.has_left ? 2u * R * 4u : 0u) + (L.has_up ? 2u * R * 4u : 0u);
+    const uint32_t bytes_u = (L.has_right ? 2u * R * 4u : 0u) + (L.has_down ? 2u * R * 4u : 0u);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(barP, 1);
+        mbar_init(barU, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (bytes_p) mbar_expect_tx(barP, bytes_p);  // first phase of both ghost barriers
+        if (bytes_u) mbar_expect_tx(barU, bytes_u);
+    }
+    for (int i = tid; i < (int)(sizeof(ClusterGhosts) / sizeof(float)); i += NT) reinterpret_cast<float *>(gh)[i] = 0.f;
+    __syncthreads();
+    cluster_sync_all();  // nobody sends into a barrier that is not initialised yet
+
+    uint32_t parP = 0, parU = 0;
+    int st = cluster_id;
+    const bool issuer = tid < 32 && elect_one();
+    auto origin = [&](int s, int &ox, int &oy) {
+        const int sty = s / stiles_x, stx = s - sty * stiles_x;
+        ox = stx * stile_x - halo + R * qx;
+        oy = sty * stile_y - halo + R * qy;
+    };
+    if (issuer && st < n_super) {
+        int ox, oy;
+        origin(st, ox, oy);
+        mbar_expect_tx(bar, kStageBytes);
+#pragma unroll
+        for (int pl = 0; pl < N_IN; ++pl) tma_load_2d(stage + pl * PLANE_F, &maps.in[pl], ox, oy, bar);
+    }
+    uint32_t parity = 0;
+    for (; st < n_super; st += n_clusters) {
+        int gx0, gy0;
+        origin(st, gx0, gy0);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+
+        Regs r;
+        {
+            const int o0 = (2 * tr) * R + 4 * lx, o1 = o0 + R;
+            auto ldrow = [&](int pl, float (&a)[4], float (&b)[4]) {
+                ld4(stage + pl * PLANE_F + o0, a);
+                ld4(stage + pl * PLANE_F + o1, b);
+            };
+            ldrow(0, r.Ix[0], r.Ix[1]);   ldrow(1, r.Iy[0], r.Iy[1]);   ldrow(2, r.gr[0], r.gr[1]);   ldrow(3, r.rc[0], r.rc[1]);
+            ldrow(4, r.u1[0], r.u1[1]);   ldrow(5, r.u2[0], r.u2[1]);   ldrow(6, r.p11[0], r.p11[1]); ldrow(7, r.p12[0], r.p12[1]);
+            ldrow(8, r.p21[0], r.p21[1]); ldrow(9, r.p22[0], r.p22[1]);
+        }
+        __syncthreads();  // the staging buffer is free again
+
+        const int sn = st + n_clusters;
+        if (issuer && sn < n_super) {
+            int ox, oy;
+            origin(sn, ox, oy);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, kStageBytes);
+#pragma unroll
+            for (int pl = 0; pl < N_IN; ++pl) tma_load_2d(stage + pl * PLANE_F, &maps.in[pl], ox, oy, bar);
+        }
+
+        const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
+        const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
+        if (border)
+            tile_iterate_cluster<true>(r, ex, gh, L, barP, barU, parP, parU, iters, k, lx, tr, gxb, gyb, cols, rows);
+        else
+            tile_iterate_cluster<false>(r, ex, gh, L, barP, barU, parP, parU, iters, k, lx, tr, gxb, gyb, cols, rows);
+
+        // valid part of my region: the halo is only on the sides that are outer sides of the super-region
+        const int x_lo = L.has_left ? 0 : halo, x_hi = L.has_right ? R : R - halo;
+        const int y_lo = L.has_up ? 0 : halo, y_hi = L.has_down ? R : R - halo;
+        const int rx = 4 * lx;
+        if (rx >= x_lo && rx < x_hi && gxb >= 0 && gxb < cols) {
+            const bool full = gxb + 3 < cols;
+            const int nc = cols - gxb;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int ry = 2 * tr + j, gy = gyb + j;
+                if (ry >= y_lo && ry < y_hi && gy >= 0 && gy < rows) {
+                    const size_t off = (size_t)gy * o_u1.pitch + gxb;
+                    store_strip(o_u1.p + off, r.u1[j][0], r.u1[j][1], r.u1[j][2], r.u1[j][3], full, nc);
+                    store_strip(o_u2.p + off, r.u2[j][0], r.u2[j][1], r.u2[j][2], r.u2[j][3], full, nc);
+                    store_strip(o_p11.p + off, r.p11[j][0], r.p11[j][1], r.p11[j][2], r.p11[j][3], full, nc);
+                    store_strip(o_p12.p + off, r.p12[j][0], r.p12[j][1], r.p12[j][2], r.p12[j][3], full, nc);
+                    store_strip(o_p21.p + off, r.p21[j][0], r.p21[j][1], r.p21[j][2], r.p21[j][3], full, nc);
+                    store_strip(o_p22.p + off, r.p22[j][0], r.p22[j][1], r.p22[j][2], r.p22[j][3], full, nc);
+                }
+            }
+        }
+    }
+    cluster_sync_all();  // no CTA leaves while a neighbour may still address its shared memory
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -716,6 +1061,66 @@ void tvl1_packed_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlan
                so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles);
 }
 
+constexpr size_t smem_cluster_bytes() {
+    return sizeof(float) * (size_t)(N_IN * R * R + 4 * EX_F) + sizeof(ClusterGhosts) + 64;
+}
+
+// Clusters that can be co-resident (GPC boundaries cap it below SMs / cluster size); cached per shape.
+static int cluster_max_active(int cx, int cy, int num_sms) {
+    static int cache[3][3] = {};
+    if (cache[cx][cy]) return cache[cx][cy];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cx * cy * (num_sms / (cx * cy)));
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem_cluster_bytes();
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = cx * cy;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_tvl1_cluster_tma, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = num_sms / (cx * cy);
+    }
+    cache[cx][cy] = n;
+    return n;
+}
+
+int tvl1_cluster_max_active(int cx, int cy, int num_sms) { return cluster_max_active(cx, cy, num_sms); }
+
+void tvl1_cluster_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                         const Tvl1Scalars &k, int iters, int num_sms, int cx, int cy) {
+    const Tvl1State &so = B.s[cur ^ 1];
+    const int halo = (iters + 3) & ~3;   // multiples of 4: 16-byte TMA box origins and vector stores
+    const int stile_x = R * cx - 2 * halo, stile_y = R * cy - 2 * halo;
+    const int stiles_x = div_up(cols, stile_x), stiles_y = div_up(rows, stile_y);
+    const int n_super = stiles_x * stiles_y;
+    const int max_cl = cluster_max_active(cx, cy, num_sms);
+    const int n_clusters = n_super < max_cl ? n_super : max_cl;
+    const double bytes = 64.0 * (double)rows * cols * iters;
+    const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;  // 64-wide boxes
+    if (!c.ok()) return;
+    c.pre(cls, bytes);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_clusters * cx * cy);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem_cluster_bytes();
+    cfg.stream = c.stream;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = cx * cy;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    c.check(cudaLaunchKernelEx(&cfg, k_tvl1_cluster_tma, *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k,
+                               iters, halo, cx, cy, stile_x, stile_y, stiles_x, n_super));
+    c.post(cls);
+}
+
 cudaError_t tvl1_blocked_init() {
     static bool done[64] = {};
     int dev = 0;
@@ -735,6 +1140,9 @@ cudaError_t tvl1_blocked_init() {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_tvl1_packed_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_packed_bytes());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_cluster_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_cluster_bytes());
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }

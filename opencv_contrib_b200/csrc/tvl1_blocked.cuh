@@ -55,4 +55,9 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
 void tvl1_packed_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                         const Tvl1Scalars &k, int iters, int num_sms);
 
+// Thread-block-cluster variant: cx x cy CTAs (2x2 or 2x1) share one super-region through DSMEM ghost exchange.
+void tvl1_cluster_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                         const Tvl1Scalars &k, int iters, int num_sms, int cx, int cy);
+int tvl1_cluster_max_active(int cx, int cy, int num_sms);
+
 }  // namespace b2f

@@ -57,8 +57,9 @@ def test_blocked_kernel_bit_identical_to_unfused(cuda_device, K):
     I0, I1, _ = synth.make_pair(203, 277, seed=3, kind="smooth")
     kw = dict(nscales=3, warps=2, epsilon=0.0, iterations=23)
     a, _ = _run(cuda_device, I0, I1, path=1, **kw)
-    # 0 = scalar persistent TMA kernel, 5 = packed-FP32 (f32x2) variant, 2 = blocked kernel with plain loads
-    for path in (0, 5, 2):
+    # 0 = scalar persistent TMA kernel, 5 = packed-FP32 (f32x2) variant, 6 / 7 = 2x2 / 2x1 thread-block clusters with
+    # DSMEM ghost exchange, 2 = blocked kernel with plain loads
+    for path in (0, 5, 6, 7, 2):
         for graph in (0, 1):
             b, _ = _run(cuda_device, I0, I1, path=path, fused=K, graph=graph, **kw)
             assert np.array_equal(a, b), (path, K, graph, float(np.abs(a - b).max()))
