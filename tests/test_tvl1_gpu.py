@@ -59,7 +59,9 @@ def test_blocked_kernel_bit_identical_to_unfused(cuda_device, K):
     a, _ = _run(cuda_device, I0, I1, path=1, **kw)
     # 0 = scalar persistent TMA kernel, 5 = packed-FP32 (f32x2) variant, 6 / 7 = 2x2 / 2x1 thread-block clusters with
     # DSMEM ghost exchange, 2 = blocked kernel with plain loads
-    for path in (0, 5, 6, 7, 2):
+    import os
+    paths = (0, 5, 2) if os.environ.get("B2F_SKIP_CLUSTER") else (0, 5, 6, 7, 2)
+    for path in paths:
         for graph in (0, 1):
             b, _ = _run(cuda_device, I0, I1, path=path, fused=K, graph=graph, **kw)
             assert np.array_equal(a, b), (path, K, graph, float(np.abs(a - b).max()))
