@@ -528,6 +528,15 @@ __global__ void __launch_bounds__(256) k_farn_iter(Stack5 Min, Stack5 Mout, Stac
 //   R0 / M / flow   move as float4.
 // Block = 64 x 32 output pixels, 256 threads, 5*32*(64+2K)*4 B shared memory.
 // ------------------------------------------------------------------------------------------
+// sum of the first N elements as a balanced tree (short dependency chain)
+template <int N, int M>
+__device__ __forceinline__ float box_first(const float (&v)[M]) {
+    static_assert(N == 13 && M >= N, "window of 13");
+    const float a = (v[0] + v[1]) + (v[2] + v[3]), b = (v[4] + v[5]) + (v[6] + v[7]);
+    const float c = (v[8] + v[9]) + (v[10] + v[11]);
+    return ((a + b) + c) + v[12];
+}
+
 constexpr int FT_W = 64, FT_H = 32;
 
 template <int K, bool GAUSS, bool QUAD, int NT = 256>
@@ -568,15 +577,24 @@ __global__ void __launch_bounds__(NT) k_farn_iter_fast(Stack5 Min, Stack5 Mout, 
             for (int q = 0; q < WIN; ++q) v[q] = __ldg(colp + (size_t)clampi(yb + q, 0, rows - 1) * Min.pitch);
         }
         float *dst = sm + ((size_t)pl * FT_H + half * HALF) * SW + i;
+        if (GAUSS) {
 #pragma unroll
-        for (int o = 0; o < HALF; ++o) {
-            float acc = GAUSS ? v[o + K] * gk[0] : v[o + K];
+            for (int o = 0; o < HALF; ++o) {
+                float acc = v[o + K] * gk[0];
 #pragma unroll
-            for (int j = 1; j <= K; ++j) {
-                const float s2 = v[o + K - j] + v[o + K + j];
-                acc = GAUSS ? acc + s2 * gk[j] : acc + s2;
+                for (int j = 1; j <= K; ++j) acc = acc + (v[o + K - j] + v[o + K + j]) * gk[j];
+                dst[o * SW] = acc;
             }
-            dst[o * SW] = acc;
+        } else {
+            // box window: running sum (one window of 2K+1 adds, then +new -old per output) instead of 2K adds per
+            // output -- 44 instead of 192 additions for 16 outputs; the CPU reference slides its vertical sums too
+            float acc = box_first<2 * K + 1>(v);
+            dst[0] = acc;
+#pragma unroll
+            for (int o = 1; o < HALF; ++o) {
+                acc = acc + (v[o + 2 * K] - v[o - 1]);
+                dst[o * SW] = acc;
+            }
         }
     }
     __syncthreads();
@@ -600,15 +618,22 @@ __global__ void __launch_bounds__(NT) k_farn_iter_fast(Stack5 Min, Stack5 Mout, 
                 if (4 * c + 2 < 4 + 2 * K + 2) w[4 * c + 2] = t.z;
                 if (4 * c + 3 < 4 + 2 * K + 2) w[4 * c + 3] = t.w;
             }
+            if (GAUSS) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float acc = GAUSS ? w[e + K] * gk[0] : w[e + K];
+                for (int e = 0; e < 4; ++e) {
+                    float acc = w[e + K] * gk[0];
 #pragma unroll
-                for (int i = 1; i <= K; ++i) {
-                    const float s2 = w[e + K - i] + w[e + K + i];
-                    acc = GAUSS ? acc + s2 * gk[i] : acc + s2;
+                    for (int i = 1; i <= K; ++i) acc = acc + (w[e + K - i] + w[e + K + i]) * gk[i];
+                    res[pl][e] = acc;
                 }
-                res[pl][e] = GAUSS ? acc : acc * box_inv;
+            } else {
+                float acc = box_first<2 * K + 1>(w);
+                res[pl][0] = acc * box_inv;
+#pragma unroll
+                for (int e = 1; e < 4; ++e) {
+                    acc = acc + (w[e + 2 * K] - w[e - 1]);
+                    res[pl][e] = acc * box_inv;
+                }
             }
         }
         float fx[4], fy[4];
@@ -759,15 +784,22 @@ __global__ void __launch_bounds__(TNT, 1)
 #pragma unroll
             for (int q = 0; q < 16 + 2 * K; ++q) v[q] = col[q * TB_W];
             float *dst = sums + (pl * TT + strip * 16) * TSW + i;
+            if (GAUSS) {
 #pragma unroll
-            for (int o = 0; o < 16; ++o) {
-                float acc = GAUSS ? v[o + K] * gk[0] : v[o + K];
+                for (int o = 0; o < 16; ++o) {
+                    float acc = v[o + K] * gk[0];
 #pragma unroll
-                for (int j = 1; j <= K; ++j) {
-                    const float s2 = v[o + K - j] + v[o + K + j];
-                    acc = GAUSS ? acc + s2 * gk[j] : acc + s2;
+                    for (int j = 1; j <= K; ++j) acc = acc + (v[o + K - j] + v[o + K + j]) * gk[j];
+                    dst[o * TSW] = acc;
                 }
-                dst[o * TSW] = acc;
+            } else {
+                float acc = box_first<2 * K + 1>(v);
+                dst[0] = acc;
+#pragma unroll
+                for (int o = 1; o < 16; ++o) {
+                    acc = acc + (v[o + 2 * K] - v[o - 1]);
+                    dst[o * TSW] = acc;
+                }
             }
         }
         __syncthreads();  // sums complete, inbuf free
@@ -797,15 +829,22 @@ __global__ void __launch_bounds__(TNT, 1)
                     if (4 * c + 2 < 4 + 2 * K + 2) w[4 * c + 2] = tq.z;
                     if (4 * c + 3 < 4 + 2 * K + 2) w[4 * c + 3] = tq.w;
                 }
+                if (GAUSS) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float acc = GAUSS ? w[e + K] * gk[0] : w[e + K];
+                    for (int e = 0; e < 4; ++e) {
+                        float acc = w[e + K] * gk[0];
 #pragma unroll
-                    for (int i = 1; i <= K; ++i) {
-                        const float s2 = w[e + K - i] + w[e + K + i];
-                        acc = GAUSS ? acc + s2 * gk[i] : acc + s2;
+                        for (int i = 1; i <= K; ++i) acc = acc + (w[e + K - i] + w[e + K + i]) * gk[i];
+                        res[pl][e] = acc;
                     }
-                    res[pl][e] = GAUSS ? acc : acc * box_inv;
+                } else {
+                    float acc = box_first<2 * K + 1>(w);
+                    res[pl][0] = acc * box_inv;
+#pragma unroll
+                    for (int e = 1; e < 4; ++e) {
+                        acc = acc + (w[e + 2 * K] - w[e - 1]);
+                        res[pl][e] = acc * box_inv;
+                    }
                 }
             }
             float fx[4], fy[4];
