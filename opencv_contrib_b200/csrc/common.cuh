@@ -219,6 +219,8 @@ struct b2f_handle {
     virtual size_t workspace_bytes(int rows, int cols, int type) = 0;
     // does calc() read the caller's `flow` before writing it (useInitialFlow / OPTFLOW_USE_INITIAL_FLOW)?
     virtual bool reads_flow() const { return false; }
+    // statistics that live on the device until the caller's stream has been synchronised (b2f_get_stats calls this)
+    virtual void refresh_stats() {}
 
     b2f::Ctx make_ctx(cudaStream_t s);
     int finish(b2f::Ctx &ctx, cudaStream_t s);  // maps ctx.err -> status, NULL-stream sync

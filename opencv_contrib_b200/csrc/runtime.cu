@@ -284,6 +284,7 @@ const char *b2f_version(void) { return "b200flow 0.1 (sm_100a)"; }
 int b2f_get_stats(b2f_handle *h, b2f_stats *out) {
     if (!h || !out) return B2F_BAD_ARG;
     h->collect_profile();
+    h->refresh_stats();
     *out = h->stats;
     return B2F_OK;
 }

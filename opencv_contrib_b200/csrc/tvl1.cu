@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(256) k_tvl1_warp_sep(Plane I0, Plane I1, Plane
 // Used for gamma != 0, for the epsilon > 0 cadence and as the cross-check for the blocked kernel.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_tvl1_estimate_u(Tvl1Planes P, int rows, int cols, Tvl1Scalars k,
-                                                         int calc_error, double *__restrict__ partials) {
+                                                         int calc_error, double *__restrict__ partials,
+                                                         const int *__restrict__ enable) {
+    if (enable && __ldg(enable) == 0) return;  // device-side convergence loop: this body does not end with a sample
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     float err = 0.f;
@@ -266,7 +268,9 @@ __global__ void __launch_bounds__(256) k_tvl1_estimate_u(Tvl1Planes P, int rows,
     }
 }
 
-__global__ void __launch_bounds__(256) k_tvl1_estimate_dual(Tvl1Planes P, int rows, int cols, Tvl1Scalars k) {
+__global__ void __launch_bounds__(256) k_tvl1_estimate_dual(Tvl1Planes P, int rows, int cols, Tvl1Scalars k,
+                                                            const int *__restrict__ enable) {
+    if (enable && __ldg(enable) == 0) return;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= cols || y >= rows) return;
@@ -328,7 +332,8 @@ __global__ void __launch_bounds__(256) k_tvl1_median(Plane a_in, Plane b_in, Pla
 
 // Fixed-order final reduction of the per-block partial sums (single block).
 __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, int n,
-                                                         double *__restrict__ out) {
+                                                         double *__restrict__ out, const int *__restrict__ enable) {
+    if (enable && __ldg(enable) == 0) return;
     __shared__ double sm[256];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) s += partials[i];
@@ -339,6 +344,73 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restric
         __syncthreads();
     }
     if (threadIdx.x == 0) *out = sm[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-side convergence loop (epsilon > 0).  The reference decides on the HOST, after a blocking copy of the
+// error sum, whether to go on (tvl1flow.cpp:357-380); here the same cadence runs on the GPU: the loop is a WHILE
+// conditional node of the CUDA graph, its body is
+//     [blocked pass A: ia iterations, state set 0 -> 1] [blocked pass B: ib iterations, 1 -> 0]      (unsampled stretch)
+//     [estimate_u with error image] [fixed-order reduction] [estimate_dual]                          (sampled iteration)
+//     [k_eps_step: book-keeping of the reference's (n, error, prevError), plan of the next body, loop condition]
+// with every count read from EpsState at run time (two passes keep the current state set fixed, so every pointer
+// in the graph is static; a stretch of m <= 16 unsampled iterations is split ceil(m/2) + floor(m/2), a zero-iteration
+// pass B is a plain copy back).  No host synchronisation, no host decision.
+// ---------------------------------------------------------------------------------------------
+struct EpsState {
+    double error, prevError, scaledEps, pe_after;
+    int n, iterations;
+    int ia, ib;       // iterations of pass A / B of the next body (-1: the body has no unsampled stretch)
+    int m;            // ia + ib
+    int sample;       // the next body ends with a sampled iteration
+    unsigned long long iters_total;  // statistics: iterations run since k_eps_reset
+};
+enum { EPS_STRETCH_MAX = 16 };
+
+__device__ __forceinline__ void eps_plan(EpsState &s) {
+    int m = 0;
+    double pe = s.prevError;
+    // unsampled iterations ahead: calcError = (n & 1) && prevError < scaledEps; each unsampled one lowers prevError
+    while (s.n + m < s.iterations && m < EPS_STRETCH_MAX && !(((s.n + m) & 1) && pe < s.scaledEps)) {
+        pe -= s.scaledEps;
+        ++m;
+    }
+    s.m = m;
+    s.pe_after = pe;
+    s.sample = (s.n + m < s.iterations && ((s.n + m) & 1) && pe < s.scaledEps) ? 1 : 0;
+    s.ia = m ? (m + 1) / 2 : -1;
+    s.ib = m ? m - (m + 1) / 2 : -1;
+}
+
+__global__ void k_eps_reset(EpsState *s) { s->iters_total = 0ull; }
+
+__global__ void k_eps_begin(EpsState *s, double scaledEps, int iterations, cudaGraphConditionalHandle h) {
+    s->n = 0;
+    s->iterations = iterations;
+    s->scaledEps = scaledEps;
+    s->prevError = 0.0;                 // tvl1flow.cpp:358
+    s->error = 1.7976931348623157e308;  // DBL_MAX
+    const bool go = s->error > s->scaledEps && s->n < s->iterations;
+    if (go) eps_plan(*s);
+    cudaGraphSetConditional(h, go ? 1u : 0u);
+}
+
+__global__ void k_eps_step(EpsState *s, const double *__restrict__ err_dev, cudaGraphConditionalHandle h) {
+    // account for the body that has just run
+    if (s->m) {
+        s->n += s->m;
+        s->prevError = s->pe_after;
+        s->error = 1.7976931348623157e308;
+    }
+    if (s->sample) {
+        s->error = *err_dev;
+        s->prevError = s->error;
+        s->n += 1;
+    }
+    s->iters_total += (unsigned long long)(s->m + s->sample);
+    const bool go = s->error > s->scaledEps && s->n < s->iterations;
+    if (go) eps_plan(*s);
+    cudaGraphSetConditional(h, go ? 1u : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,6 +426,7 @@ public:
     explicit Tvl1Engine(const b2f_tvl1_params &p) : P(p) { algo = ALGO_TVL1; }
     ~Tvl1Engine() override {
         if (err_host) cudaFreeHost(err_host);
+        if (iters_host_) cudaFreeHost(iters_host_);
         free(tma_maps_);
         destroy_graph();
     }
@@ -387,6 +460,7 @@ private:
         float *shared[16] = {};     // level-shared planes, viewed with per-level pitch
         double *partials = nullptr;
         double *err_dev = nullptr;
+        EpsState *eps = nullptr;   // device-side convergence loop
         int rows = 0, cols = 0;
         bool gamma = false;
         int nscales_param = 0;
@@ -426,6 +500,20 @@ private:
     Plane shared_plane(int idx, int cols) const { return Plane{L_.shared[idx], plane_pitch(cols)}; }
     void solve(Ctx &c, bool allow_sync);
     void proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync);
+    // epsilon > 0 inside a CUDA graph: the reference's adaptive loop as a WHILE conditional node (see EpsState)
+    bool device_loop_ok() const {
+        return P.epsilon > 0.0 && !L_.gamma && tma_ok_ && (knobs.kernel_path == 0 || knobs.kernel_path == 3) &&
+               median_filtering == 1 && !getenv("B2F_TVL1_HOST_LOOP");
+    }
+    void device_eps_loop(Ctx &c, int s, const Tvl1Planes &T, const Tvl1BlockedPlanes &B, const Tvl1Scalars &k,
+                         double scaledEps, dim3 grid, dim3 block, int nblocks, int rows, int cols);
+    unsigned long long *iters_host_ = nullptr;  // pinned: EpsState::iters_total of the last device-loop solve
+    bool device_loop_used_ = false;
+public:
+    void refresh_stats() override {
+        if (device_loop_used_ && iters_host_) stats.iterations_run = static_cast<int>(*iters_host_);
+    }
+private:
 };
 
 enum { SH_I1WX = 0, SH_I1WY, SH_GRAD, SH_RHO, SH_P11, SH_P12, SH_P21, SH_P22, SH_P31, SH_P32,
@@ -479,6 +567,7 @@ size_t Tvl1Engine::layout(int rows, int cols, bool counting, Layout &L) {
     const int nblocks = div_up(cols, 32) * div_up(rows, 8);
     L.partials = static_cast<double *>(A.bytes(sizeof(double) * nblocks));
     L.err_dev = static_cast<double *>(A.bytes(sizeof(double) * 4));
+    L.eps = static_cast<EpsState *>(A.bytes(sizeof(EpsState)));
     return A.used();
 }
 
@@ -535,6 +624,51 @@ void Tvl1Engine::blocked_planes(int s, Tvl1BlockedPlanes &B) const {
     B.s[1].u1 = shared_plane(SH_U1B, cols); B.s[1].u2 = shared_plane(SH_U2B, cols);
     B.s[1].p11 = shared_plane(SH_P11B, cols); B.s[1].p12 = shared_plane(SH_P12B, cols);
     B.s[1].p21 = shared_plane(SH_P21B, cols); B.s[1].p22 = shared_plane(SH_P22B, cols);
+}
+
+void Tvl1Engine::device_eps_loop(Ctx &c, int s, const Tvl1Planes &T, const Tvl1BlockedPlanes &B, const Tvl1Scalars &k,
+                                 double scaledEps, dim3 grid, dim3 block, int nblocks, int rows, int cols) {
+    if (!c.ok()) return;
+    cudaStream_t cs = c.stream;  // the capturing stream
+    cudaStreamCaptureStatus st;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t nd = 0;
+    c.check(cudaStreamGetCaptureInfo_v2(cs, &st, nullptr, &g, &deps, &nd));
+    cudaGraphConditionalHandle h;
+    if (c.ok()) c.check(cudaGraphConditionalHandleCreate(&h, g, 0, 0));
+    if (!c.ok()) return;
+    B2F_LAUNCH(c, CLS_REDUCE, 0.0, k_eps_begin, dim3(1), dim3(1), 0, L_.eps, scaledEps, P.iterations, h);
+    c.check(cudaStreamGetCaptureInfo_v2(cs, &st, nullptr, &g, &deps, &nd));
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.conditional.handle = h;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node = nullptr;
+    if (c.ok()) c.check(cudaGraphAddNode(&node, g, deps, nd, &np));
+    if (c.ok()) c.check(cudaStreamUpdateCaptureDependencies(cs, &node, 1, cudaStreamSetCaptureDependencies));
+    if (!c.ok()) return;
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    cudaStream_t bs = nullptr;
+    c.check(cudaStreamCreateWithFlags(&bs, cudaStreamNonBlocking));
+    if (!c.ok()) return;
+    c.check(cudaStreamBeginCaptureToGraph(bs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    if (c.ok()) {
+        Ctx b = c;
+        b.stream = bs;
+        const double npx = (double)rows * cols;
+        tvl1_tma_launch_dev(b, CLS_ITER, tma_maps(s, 0), B, 0, rows, cols, k, &L_.eps->ia, num_sms_);
+        tvl1_tma_launch_dev(b, CLS_ITER, tma_maps(s, 1), B, 1, rows, cols, k, &L_.eps->ib, num_sms_);
+        B2F_LAUNCH(b, CLS_ITER, 48.0 * npx, k_tvl1_estimate_u, grid, block, 0, T, rows, cols, k, 1, L_.partials,
+                   &L_.eps->sample);
+        B2F_LAUNCH(b, CLS_REDUCE, 8.0 * nblocks, k_reduce_partials, dim3(1), dim3(256), 0, L_.partials, nblocks,
+                   L_.err_dev, &L_.eps->sample);
+        B2F_LAUNCH(b, CLS_ITER, 40.0 * npx, k_tvl1_estimate_dual, grid, block, 0, T, rows, cols, k, &L_.eps->sample);
+        B2F_LAUNCH(b, CLS_REDUCE, 0.0, k_eps_step, dim3(1), dim3(1), 0, L_.eps, L_.err_dev, h);
+        c.check(b.err);
+        c.check(cudaStreamEndCapture(bs, nullptr));
+    }
+    cudaStreamDestroy(bs);
 }
 
 void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
@@ -648,6 +782,11 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
             continue;
         }
 
+        if (c.capturing && device_loop_ok() && blocked_ok && use_tma && cur == 0) {  // same cadence, decided on the GPU
+            device_eps_loop(c, s, T, B, k, scaledEpsilon, grid, block, nblocks, rows, cols);
+            continue;
+        }
+
         // reference cadence (tvl1flow.cpp:357-380)
         double error = std::numeric_limits<double>::max();
         double prevError = 0.0;
@@ -673,10 +812,10 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
             }
             point_T_at(cur);
             B2F_LAUNCH(c, CLS_ITER, 48.0 * npx, k_tvl1_estimate_u, grid, block, 0, T, rows, cols, k,
-                       calcError ? 1 : 0, L_.partials);
+                       calcError ? 1 : 0, L_.partials, nullptr);
             if (calcError) {
                 B2F_LAUNCH(c, CLS_REDUCE, 8.0 * nblocks, k_reduce_partials, dim3(1), dim3(256), 0, L_.partials,
-                           nblocks, L_.err_dev);
+                           nblocks, L_.err_dev, nullptr);
                 if (allow_sync && c.ok()) {
                     c.check(cudaMemcpyAsync(err_host, L_.err_dev, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
                     c.check(cudaStreamSynchronize(c.stream));
@@ -687,7 +826,7 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
                 error = std::numeric_limits<double>::max();
                 prevError -= scaledEpsilon;
             }
-            B2F_LAUNCH(c, CLS_ITER, 40.0 * npx, k_tvl1_estimate_dual, grid, block, 0, T, rows, cols, k);
+            B2F_LAUNCH(c, CLS_ITER, 40.0 * npx, k_tvl1_estimate_dual, grid, block, 0, T, rows, cols, k, nullptr);
             c.stats->iterations_run++;
             ++n;
         }
@@ -701,6 +840,7 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
 
 void Tvl1Engine::solve(Ctx &c, bool allow_sync) {
     const int ns = L_.nscales;
+    if (c.capturing && P.epsilon > 0.0) B2F_LAUNCH(c, CLS_REDUCE, 0.0, k_eps_reset, dim3(1), dim3(1), 0, L_.eps);
     const bool use_gamma = L_.gamma;
     int u3i = 0;
     if (!P.use_initial_flow) {
@@ -770,7 +910,9 @@ int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
     }
 
     const bool fixed_schedule = !(P.epsilon > 0.0);
-    const bool want_graph = knobs.use_graph && fixed_schedule && !profiling && s != nullptr;
+    const bool dev_loop = !fixed_schedule && device_loop_ok();  // WHILE conditional nodes instead of host decisions
+    const bool want_graph = knobs.use_graph && (fixed_schedule || dev_loop) && !profiling && s != nullptr;
+    device_loop_used_ = false;
     if (want_graph) {
         const bool hit = graph_exec_ && graph_key_.rows == rows && graph_key_.cols == cols &&
                          same_params(graph_key_.P, P) &&
@@ -822,6 +964,13 @@ int Tvl1Engine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *flow, 
                 stats.class_bytes[i] += graph_class_bytes_[i];
             }
             stats.iterations_run = graph_iterations_;
+            if (dev_loop) {  // the true count lives on the device: fetch it behind the solve, read it in refresh_stats()
+                if (!iters_host_) c.check(cudaMallocHost(&iters_host_, sizeof(unsigned long long)));
+                if (c.ok())
+                    c.check(cudaMemcpyAsync(iters_host_, &L_.eps->iters_total, sizeof(unsigned long long),
+                                            cudaMemcpyDeviceToHost, s));
+                device_loop_used_ = c.ok();
+            }
         }
     } else {
         solve(c, true);

@@ -267,8 +267,12 @@ template <bool ELECT, int TBOX_W>
 __global__ void __launch_bounds__(NT, 1)
     k_tvl1_blocked_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12,
                        Plane o_p21, Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int tile,
-                       int tiles_x, int ntiles) {
+                       int tiles_x, int ntiles, const int *__restrict__ iters_dev) {
     constexpr int TPLANE_F = TBOX_W * R;  // floats per staged plane
+    if (iters_dev) {  // device-side convergence loop: the iteration count of this pass is decided on the GPU
+        iters = __ldg(iters_dev);
+        if (iters < 0) return;  // pass not needed (every thread takes the same branch)
+    }
     extern __shared__ __align__(1024) float smem[];
     float *stage = smem;
     float *ex = smem + N_IN * TPLANE_F;
@@ -1033,15 +1037,29 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
     const TmaMaps *m = static_cast<const TmaMaps *>(maps) + (aligned ? 1 : 0);
     if (aligned)
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R>), dim3(grid), dim3(NT), smem_tma_bytes(R), *m, so.u1,
-                   so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles);
+                   so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr);
     else if (elect)
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, TBOX_WIDE>), dim3(grid), dim3(NT),
                    smem_tma_bytes(TBOX_WIDE), *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
-                   halo, tile, tiles_x, ntiles);
+                   halo, tile, tiles_x, ntiles, nullptr);
     else
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<false, TBOX_WIDE>), dim3(grid), dim3(NT),
                    smem_tma_bytes(TBOX_WIDE), *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
-                   halo, tile, tiles_x, ntiles);
+                   halo, tile, tiles_x, ntiles, nullptr);
+}
+
+// One pass whose iteration count (0..8; negative = skip the pass) is read from device memory at run time: fixed
+// geometry (8-pixel halo, 48-pixel tiles, 64-wide boxes) so the launch can sit in a CUDA graph's while-loop body.
+void tvl1_tma_launch_dev(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                         const Tvl1Scalars &k, const int *iters_dev, int num_sms) {
+    const Tvl1State &so = B.s[cur ^ 1];
+    const int halo = 8, tile = R - 2 * halo;
+    const int tiles_x = div_up(cols, tile), tiles_y = div_up(rows, tile);
+    const int ntiles = tiles_x * tiles_y;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;
+    B2F_LAUNCH(c, cls, 0.0, (k_tvl1_blocked_tma<true, R>), dim3(grid), dim3(NT), smem_tma_bytes(R), *m, so.u1, so.u2,
+               so.p11, so.p12, so.p21, so.p22, rows, cols, k, 0, halo, tile, tiles_x, ntiles, iters_dev);
 }
 
 constexpr size_t smem_packed_bytes() { return sizeof(float) * (size_t)(N_IN * R * R) + sizeof(float4) * 4 * PEX_F4 + 64; }

@@ -51,6 +51,10 @@ bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int row
 void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                      const Tvl1Scalars &k, int iters, int num_sms, bool elect = true);
 
+// Same kernel, iteration count read from device memory when the pass runs (device-side convergence loop).
+void tvl1_tma_launch_dev(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                         const Tvl1Scalars &k, const int *iters_dev, int num_sms);
+
 // Packed-FP32 (f32x2) persistent TMA kernel, the default path; iters <= TVL1_KMAX.
 void tvl1_packed_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                         const Tvl1Scalars &k, int iters, int num_sms);

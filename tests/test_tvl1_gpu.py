@@ -88,6 +88,23 @@ def test_default_epsilon_cadence_matches_model(cuda_device):
     assert alg.getStats()["iterations_run"] == sum(sum(t) for t in tr)
 
 
+def test_device_side_convergence_loop_equals_host_loop(cuda_device):
+    """epsilon > 0 on a real stream: the reference's adaptive stopping rule runs as a WHILE conditional node of the CUDA
+    graph (no host synchronisation inside calc); on the legacy default stream / without a graph the host decides like
+    the reference does (tvl1flow.cpp:357-380).  Same cadence, same arithmetic -> same bits, same iteration count."""
+    import torch
+    I0, I1, _ = synth.make_pair(150, 190, seed=6, kind="smooth")
+    for kw in (dict(nscales=3, warps=3, epsilon=0.01, iterations=100), dict(nscales=2, warps=2, epsilon=0.05, iterations=37),
+               dict()):  # the reference's create() defaults
+        host, a_host = _run(cuda_device, I0, I1, graph=0, **kw)
+        side = torch.cuda.Stream(device=cuda_device)
+        dev, a_dev = _run(cuda_device, I0, I1, graph=1, stream=side, **kw)
+        assert np.array_equal(host, dev), float(np.abs(host - dev).max())
+        assert a_dev.getStats()["iterations_run"] == a_host.getStats()["iterations_run"] > 0
+        again, _ = _run(cuda_device, I0, I1, graph=1, stream=side, **kw)
+        assert np.array_equal(again, dev)
+
+
 def test_gamma_illumination_path(cuda_device):
     # gamma != 0 is chaotic (1e-7 input noise moves the model by ~0.1 px at a few pixels), so the
     # tolerance is statistical
