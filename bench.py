@@ -355,23 +355,27 @@ def single_stream_roofline(workload: str, pairs, flow_views, B: int):
     path, as in production) so that launch times, share and throughput describe one execution mode."""
     import torch
     alg = make_alg(workload)
-    alg.calc(*pairs[0], flow_views[0])
+    side = torch.cuda.Stream()  # a real stream: the legacy default stream takes the no-graph, device-synchronising path
     torch.cuda.synchronize()
-    # throughput of the single-stream mode
-    n1 = min(B, 8)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(n1):
-        alg.calc(*pairs[i], flow_views[i])
-    e1.record()
-    torch.cuda.synchronize()
-    value_1 = 1000.0 * n1 / e0.elapsed_time(e1)
-    # per-launch events
-    alg.setProfiling(True)
-    alg.resetStats()
-    n_prof = min(3, B)
-    for i in range(n_prof):
-        alg.calc(*pairs[i], flow_views[i])
+    with torch.cuda.stream(side):
+        alg.calc(*pairs[0], flow_views[0], side)
+        side.synchronize()
+        # throughput of the single-stream mode
+        n1 = min(B, 8)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for i in range(n1):
+            alg.calc(*pairs[i], flow_views[i], side)
+        e1.record(side)
+        side.synchronize()
+        value_1 = 1000.0 * n1 / e0.elapsed_time(e1)
+        # per-launch events
+        alg.setProfiling(True)
+        alg.resetStats()
+        n_prof = min(3, B)
+        for i in range(n_prof):
+            alg.calc(*pairs[i], flow_views[i], side)
+        side.synchronize()
     torch.cuda.synchronize()
     st = alg.getStats()
     alg.setProfiling(False)
