@@ -7,8 +7,8 @@
 // Deliberate arithmetic choices (documented in DESIGN.md, covered by the tolerance tests):
 //   * -rho/grad is -rho * rcp.approx(grad) (MUFU.RCP, <= 2 ulp) instead of an IEEE divide, and the
 //     three-way threshold test is written as the equivalent clamp (see tvl1_threshold);
-//   * hypotf(a,b) is sqrt.approx(a*a + b*b) and the dual normalisation multiplies by rcp.approx
-//     instead of IEEE divides (see tvl1_update_p2);
+//   * hypotf(a,b) is sqrt.approx(a*a + b*b) and the dual normalisation multiplies by a shared
+//     rcp.approx instead of IEEE divides (see tvl1_update_p2);
 //   * the divergence at the first row/column uses a zero ghost value, (p - 0) + (q - q_up), where
 //     the reference writes p + q - q_up: same value up to one rounding on that column only.
 #pragma once
@@ -54,15 +54,20 @@ __device__ __forceinline__ void tvl1_update_u(const Tvl1Scalars &k, float Ix, fl
 }
 
 // Dual update of both flow components of one pixel (estimateDualVariablesKernel, tvl1flow.cu:313-348).
-// ux*, uy* are the forward differences (0 on the last column / row).  Each normalisation 1/(1 + taut*g) is one
-// MUFU.RCP: the kernel is bound by FP32 issue (35 -> 31 FP32 instructions per pixel-iteration with the two-FMA rho
-// above), while the SFU pipe has room for the fourth MUFU (round 1 shared one reciprocal through three extra FMULs).
+// ux*, uy* are the forward differences (0 on the last column / row).  The two normalisations
+// 1/(1 + taut*g1), 1/(1 + taut*g2) share ONE reciprocal: r = 1/(a1*a2), inv1 = r*a2, inv2 = r*a1 (a1, a2 >= 1).
+// The SFU path (16 lanes/SM on B200, fed through the MIO queue together with LDS / STS / SHFL) is the first thing
+// to saturate in the dual half iteration: measured in round 2, a fourth MUFU per pixel instead of these three FMULs
+// makes the kernel 6 % SLOWER (mio_throttle stalls 0.86 -> 1.49 per issue, ncu) although it executes 6 % fewer
+// instructions.
 __device__ __forceinline__ void tvl1_update_p2(float taut, float ux1, float uy1, float ux2, float uy2, float &p11,
                                                float &p12, float &p21, float &p22) {
     const float g1 = sqrt_approx(__fmaf_rn(ux1, ux1, __fmul_rn(uy1, uy1)));
     const float g2 = sqrt_approx(__fmaf_rn(ux2, ux2, __fmul_rn(uy2, uy2)));
-    const float inv1 = rcp_approx(__fmaf_rn(taut, g1, 1.0f));
-    const float inv2 = rcp_approx(__fmaf_rn(taut, g2, 1.0f));
+    const float a1 = __fmaf_rn(taut, g1, 1.0f);
+    const float a2 = __fmaf_rn(taut, g2, 1.0f);
+    const float r = rcp_approx(__fmul_rn(a1, a2));
+    const float inv1 = __fmul_rn(r, a2), inv2 = __fmul_rn(r, a1);
     p11 = __fmul_rn(__fmaf_rn(taut, ux1, p11), inv1);
     p12 = __fmul_rn(__fmaf_rn(taut, uy1, p12), inv1);
     p21 = __fmul_rn(__fmaf_rn(taut, ux2, p21), inv2);
@@ -143,8 +148,9 @@ __device__ __forceinline__ void tvl1_update_p2_x2(float taut, f2 ux1, f2 uy1, f2
     const f2 t = splat2(taut), one = splat2(1.0f);
     const f2 a1 = fma2(t, g1, one);
     const f2 a2 = fma2(t, g2, one);
-    const f2 inv1 = make_float2(rcp_approx(a1.x), rcp_approx(a1.y));
-    const f2 inv2 = make_float2(rcp_approx(a2.x), rcp_approx(a2.y));
+    const f2 m = mul2(a1, a2);
+    const f2 r = make_float2(rcp_approx(m.x), rcp_approx(m.y));
+    const f2 inv1 = mul2(r, a2), inv2 = mul2(r, a1);
     p11 = mul2(fma2(t, ux1, p11), inv1);
     p12 = mul2(fma2(t, uy1, p12), inv1);
     p21 = mul2(fma2(t, ux2, p21), inv2);
