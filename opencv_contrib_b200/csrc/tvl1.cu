@@ -45,8 +45,11 @@ __global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= cols || y >= rows) return;
 
-    const float u1 = u1p.at(y, x);
-    const float u2 = u2p.at(y, x);
+    // all three streaming operands first: the I0 load used to sit behind the first three stores (possible aliasing
+    // kept the compiler from hoisting it), a third dependent memory round trip per thread
+    const float u1 = __ldg(&u1p.at(y, x));
+    const float u2 = __ldg(&u2p.at(y, x));
+    const float I0v = __ldg(&I0.at(y, x));
     const float wx = x + u1;
     const float wy = y + u2;
     const float fx = floorf(wx), fy = floorf(wy);
@@ -114,8 +117,34 @@ __global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p
     I1wx.at(y, x) = Ix;
     I1wy.at(y, x) = Iy;
     grad.at(y, x) = __fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix));
-    const float I0v = I0.at(y, x);
     rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
+}
+
+#ifndef WARP_SEP_MIN_BLOCKS
+#define WARP_SEP_MIN_BLOCKS 6
+#endif
+// Border pixels of the warp (window touches the image edge): clamp every tap, then take the clamped-neighbour gradient
+// at the clamped tap (point / clamp texture semantics of tvl1flow.cu:106-164).  A real call on purpose.
+__device__ __noinline__ void warp_border_taps(const Plane I1, int rows, int cols, int ix, int iy, const float (&kx)[4],
+                                              const float (&ky)[4], float &sum, float &sumx, float &sumy) {
+    sum = 0.f; sumx = 0.f; sumy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cy = clampi(iy + j, 0, rows - 1);
+        const int cyp = min(cy + 1, rows - 1), cym = max(cy - 1, 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cx = clampi(ix + i, 0, cols - 1);
+            const int cxp = min(cx + 1, cols - 1), cxm = max(cx - 1, 0);
+            const float w = kx[i] * ky[j];
+            const float v = __ldg(&I1.at(cy, cx));
+            const float gx = 0.5f * (__ldg(&I1.at(cy, cxp)) - __ldg(&I1.at(cy, cxm)));
+            const float gy = 0.5f * (__ldg(&I1.at(cyp, cx)) - __ldg(&I1.at(cym, cx)));
+            sum = __fmaf_rn(w, v, sum);
+            sumx = __fmaf_rn(w, gx, sumx);
+            sumy = __fmaf_rn(w, gy, sumy);
+        }
+    }
 }
 
 // Keys a = -0.5 weights of the four taps at distances (1 + t, t, 1 - t, 2 - t), t in [0, 1): the polynomials of
@@ -134,14 +163,17 @@ __device__ __forceinline__ void keys_weights(float t, float (&k)[4]) {
 // Results differ from the tap-by-tap accumulation by rounding only.  Measured on B200 (1080p 5x10x30): 1.24 ms per
 // pair against 1.26 ms -- the kernel is bound by its 36-texel gather, not by arithmetic -- so the reference-ordered
 // kernel stays the default.
-__global__ void __launch_bounds__(256) k_tvl1_warp_sep(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
+__global__ void __launch_bounds__(256, WARP_SEP_MIN_BLOCKS) k_tvl1_warp_sep(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
                                                        Plane grad, Plane rho, int rows, int cols) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= cols || y >= rows) return;
 
-    const float u1 = u1p.at(y, x);
-    const float u2 = u2p.at(y, x);
+    // all three streaming operands first: the I0 load used to sit behind the first three stores (possible aliasing
+    // kept the compiler from hoisting it), a third dependent memory round trip per thread
+    const float u1 = __ldg(&u1p.at(y, x));
+    const float u2 = __ldg(&u2p.at(y, x));
+    const float I0v = __ldg(&I0.at(y, x));
     const float wx = x + u1;
     const float wy = y + u2;
     const float fx = floorf(wx), fy = floorf(wy);
@@ -171,25 +203,7 @@ __global__ void __launch_bounds__(256) k_tvl1_warp_sep(Plane I0, Plane I1, Plane
         sumx = 0.5f * __fmaf_rn(ky[3], rx[3], __fmaf_rn(ky[2], rx[2], __fmaf_rn(ky[1], rx[1], ky[0] * rx[0])));
         sumy = 0.5f * __fmaf_rn(ky[3], r[5] - r[3], __fmaf_rn(ky[2], r[4] - r[2], __fmaf_rn(ky[1], r[3] - r[1], ky[0] * (r[2] - r[0]))));
     } else {
-        // border: clamp every tap, then take the clamped-neighbour gradient at the clamped tap
-        sum = 0.f; sumx = 0.f; sumy = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int cy = clampi(iy + j, 0, rows - 1);
-            const int cyp = min(cy + 1, rows - 1), cym = max(cy - 1, 0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int cx = clampi(ix + i, 0, cols - 1);
-                const int cxp = min(cx + 1, cols - 1), cxm = max(cx - 1, 0);
-                const float w = kx[i] * ky[j];
-                const float v = __ldg(&I1.at(cy, cx));
-                const float gx = 0.5f * (__ldg(&I1.at(cy, cxp)) - __ldg(&I1.at(cy, cxm)));
-                const float gy = 0.5f * (__ldg(&I1.at(cyp, cx)) - __ldg(&I1.at(cym, cx)));
-                sum = __fmaf_rn(w, v, sum);
-                sumx = __fmaf_rn(w, gx, sumx);
-                sumy = __fmaf_rn(w, gy, sumy);
-            }
-        }
+        warp_border_taps(I1, rows, cols, ix, iy, kx, ky, sum, sumx, sumy);  // out of line: keeps the hot path's registers low
     }
 
     const float coeff = 1.0f / wsum;
@@ -199,7 +213,6 @@ __global__ void __launch_bounds__(256) k_tvl1_warp_sep(Plane I0, Plane I1, Plane
     I1wx.at(y, x) = Ix;
     I1wy.at(y, x) = Iy;
     grad.at(y, x) = __fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix));
-    const float I0v = I0.at(y, x);
     rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
 }
 

@@ -9,12 +9,13 @@ dev = torch.device("cuda:0")
 I0, I1, gt = synth.make_pair(1080, 1920, seed=0, kind="smooth")
 d0, d1 = torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev)
 ref = None
-cases = [(int(a), int(b)) for a, b in (c.split(":") for c in (sys.argv[1:] or ["0:8", "6:8", "7:8", "6:12", "7:12"]))]
-for path, K in cases:
+cases = [tuple(int(v) for v in (c.split(":") + ["0"])[:3]) for c in (sys.argv[1:] or ["0:8", "6:8", "7:8", "6:12", "7:12"])]
+for path, K, aux in cases:
     algs = [ocb.OpticalFlowDual_TVL1_create(nscales=5, warps=10, epsilon=0.0, iterations=30) for _ in range(4)]
     for a in algs:
         a.setEngineOption("fused_iters", K)
         a.setEngineOption("kernel_path", path)
+        a.setEngineOption("aux_path", aux)
     flows = [torch.empty((1080, 1920, 2), dtype=torch.float32, device=dev) for _ in range(4)]
     streams = [torch.cuda.Stream() for _ in range(4)]
     for _ in range(2): algs[0].calc(d0, d1, flows[0])
@@ -43,5 +44,5 @@ for path, K in cases:
     a.setProfiling(True); a.resetStats(); a.calc(d0, d1, flows[0]); torch.cuda.synchronize()
     st = a.getStats(); a.setProfiling(False)
     cls = ", ".join("%s %.2f ms/%d" % (k, v["ms"], v["launches"]) for k, v in st["classes"].items() if v["launches"])
-    print("path=%d K=%d: 1 stream %.2f ms/pair (%.1f/s); 4 streams %.2f ms/pair (%.1f/s); bit-equal to first: %s | %s"
-          % (path, K, ms1, 1000 / ms1, ms4, 1000 / ms4, same, cls), flush=True)
+    print("path=%d K=%d aux=%d: 1 stream %.2f ms/pair (%.1f/s); 4 streams %.2f ms/pair (%.1f/s); bit-equal to first: %s | %s"
+          % (path, K, aux, ms1, 1000 / ms1, ms4, 1000 / ms4, same, cls), flush=True)
