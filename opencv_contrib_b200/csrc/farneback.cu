@@ -539,8 +539,8 @@ __device__ __forceinline__ float box_first(const float (&v)[M]) {
 
 constexpr int FT_W = 64, FT_H = 32;
 
-template <int K, bool GAUSS, bool QUAD, int NT = 256>
-__global__ void __launch_bounds__(NT) k_farn_iter_fast(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
+template <int K, bool GAUSS, bool QUAD, int NT = 256, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) k_farn_iter_fast(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
                                                         Plane flowy, int rows, int cols, float box_inv,
                                                         const float *__restrict__ g, int update_matrices,
                                                         int write_flow) {
@@ -1080,6 +1080,8 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FARN_TMA_SMEM));
             c.check(cudaFuncSetAttribute(k_farn_iter_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FARN_TMA_SMEM));
             attr_done[dev] = c.ok();
@@ -1236,6 +1238,12 @@ void FarnebackEngine::solve(Ctx &c) {
                                R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
                 else if (quad && wide_blocks)
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 512>), gf, dim3(512), smem_fast, Ma, Mb,
+                               R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else if (quad && knobs.aux_path == 3)  // 80 registers: 3 blocks / SM
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 256, 3>), gf, dim3(256), smem_fast, Ma, Mb,
+                               R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else if (quad && knobs.aux_path == 4)  // 64 registers: 4 blocks / SM
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 256, 4>), gf, dim3(256), smem_fast, Ma, Mb,
                                R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
                 else if (quad)
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true>), gf, dim3(256), smem_fast, Ma, Mb, R0,

@@ -661,27 +661,49 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-struct ClusterLinks {   // remote addresses (shared::cluster window) of the neighbours' ghost arrays and barriers; 0 = no neighbour
-    uint32_t right_p11L, right_p21L, right_barP;   // right neighbour: its left ghost column
-    uint32_t down_p12U, down_p22U, down_barP;      // lower neighbour: its upper ghost row
-    uint32_t left_u1R, left_u2R, left_barU;        // left neighbour: its right ghost column
-    uint32_t up_u1D, up_u2D, up_barU;              // upper neighbour: its lower ghost row
-    bool has_left, has_right, has_up, has_down;
+// Per-thread role bits (one register instead of a dozen remote addresses: those are formed with one MAPA at send time).
+enum {
+    CR_LEFT = 1,     // lx == 0  and a left neighbour exists:  reads the left ghost column, sends its first column of u
+    CR_UP = 2,       // tr == 0  and an upper neighbour exists: reads the upper ghost row,  sends its first row of u
+    CR_RIGHT = 4,    // lx == 15 and a right neighbour exists: reads the right ghost column, sends its last column of p
+    CR_DOWN = 8,     // tr == 31 and a lower neighbour exists: reads the lower ghost row,   sends its last row of p
+    CR_WAIT_P = 16,  // this CTA receives ghosts for the primal update (it has a left or an upper neighbour)
+    CR_WAIT_U = 32,  // this CTA receives ghosts for the dual update (right or lower neighbour)
+    CR_ARM = 64      // thread 0: re-arms the ghost barriers
 };
 
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_A:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_A;\n\t"
+        "bra WAIT_LOOP_A;\n\t"
+        "DONE_A:\n\t"
+        "}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t bar_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+
 // K iterations with ghost exchange.  Same arithmetic, same operand order per pixel as tile_iterate.
+// gh_a / barP_a / barU_a: shared-window addresses of this CTA's ghost block and ghost barriers (the neighbours' copies
+// sit at the same offsets of THEIR windows: mapa).  nb_*: cluster ranks of the four neighbours.
 template <bool BORDER>
-__device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, ClusterGhosts *gh, const ClusterLinks &L,
-                                                     uint64_t *barP, uint64_t *barU, uint32_t &parP, uint32_t &parU,
-                                                     int iters, const Tvl1Scalars k, int lx, int tr, int gxb, int gyb, int W,
-                                                     int H) {
+__device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, const ClusterGhosts *gh, uint32_t gh_a,
+                                                     uint32_t barP_a, uint32_t barU_a, uint32_t role, uint32_t rank,
+                                                     uint32_t cluster_x, uint32_t bytes_p, uint32_t bytes_u,
+                                                     uint32_t &parP, uint32_t &parU, int iters, const Tvl1Scalars k, int lx,
+                                                     int tr, int gxb, int gyb, int W, int H) {
     float *ex_u1 = ex, *ex_u2 = ex + EX_F, *ex_p12 = ex + 2 * EX_F, *ex_p22 = ex + 3 * EX_F;
     const int mine = tr * R + 4 * lx;
     const int up = max(tr - 1, 0) * R + 4 * lx;
     const int dn = min(tr + 1, 31) * R + 4 * lx;
-    const bool wait_p = L.has_left || L.has_up, wait_u = L.has_right || L.has_down;
-    const uint32_t bytes_p = (L.has_left ? 2u * R * 4u : 0u) + (L.has_up ? 2u * R * 4u : 0u);
-    const uint32_t bytes_u = (L.has_right ? 2u * R * 4u : 0u) + (L.has_down ? 2u * R * 4u : 0u);
+    constexpr uint32_t OFF_P11L = offsetof(ClusterGhosts, p11L), OFF_P21L = offsetof(ClusterGhosts, p21L);
+    constexpr uint32_t OFF_P12U = offsetof(ClusterGhosts, p12U), OFF_P22U = offsetof(ClusterGhosts, p22U);
+    constexpr uint32_t OFF_U1R = offsetof(ClusterGhosts, u1R), OFF_U2R = offsetof(ClusterGhosts, u2R);
+    constexpr uint32_t OFF_U1D = offsetof(ClusterGhosts, u1D), OFF_U2D = offsetof(ClusterGhosts, u2D);
 
 #pragma unroll
     for (int j = 0; j < 2; ++j)
@@ -689,34 +711,38 @@ __device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, Cluster
         for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
 
     auto send_p = [&]() {  // my last column / last row of the dual variables -> right / lower neighbour
-        if (L.has_right && lx == 15) {
+        if (role & CR_RIGHT) {
+            const uint32_t g = cluster_map(gh_a, rank + 1), b = cluster_map(barP_a, rank + 1);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                st_async_f32(L.right_p11L + 4u * (2 * tr + j), r.p11[j][3], L.right_barP);
-                st_async_f32(L.right_p21L + 4u * (2 * tr + j), r.p21[j][3], L.right_barP);
+                st_async_f32(g + OFF_P11L + 4u * (2 * tr + j), r.p11[j][3], b);
+                st_async_f32(g + OFF_P21L + 4u * (2 * tr + j), r.p21[j][3], b);
             }
         }
-        if (L.has_down && tr == 31) {
+        if (role & CR_DOWN) {
+            const uint32_t g = cluster_map(gh_a, rank + cluster_x), b = cluster_map(barP_a, rank + cluster_x);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                st_async_f32(L.down_p12U + 4u * (4 * lx + i), r.p12[1][i], L.down_barP);
-                st_async_f32(L.down_p22U + 4u * (4 * lx + i), r.p22[1][i], L.down_barP);
+                st_async_f32(g + OFF_P12U + 4u * (4 * lx + i), r.p12[1][i], b);
+                st_async_f32(g + OFF_P22U + 4u * (4 * lx + i), r.p22[1][i], b);
             }
         }
     };
     auto send_u = [&]() {  // my first column / first row of the flow -> left / upper neighbour
-        if (L.has_left && lx == 0) {
+        if (role & CR_LEFT) {
+            const uint32_t g = cluster_map(gh_a, rank - 1), b = cluster_map(barU_a, rank - 1);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                st_async_f32(L.left_u1R + 4u * (2 * tr + j), r.u1[j][0], L.left_barU);
-                st_async_f32(L.left_u2R + 4u * (2 * tr + j), r.u2[j][0], L.left_barU);
+                st_async_f32(g + OFF_U1R + 4u * (2 * tr + j), r.u1[j][0], b);
+                st_async_f32(g + OFF_U2R + 4u * (2 * tr + j), r.u2[j][0], b);
             }
         }
-        if (L.has_up && tr == 0) {
+        if (role & CR_UP) {
+            const uint32_t g = cluster_map(gh_a, rank - cluster_x), b = cluster_map(barU_a, rank - cluster_x);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                st_async_f32(L.up_u1D + 4u * (4 * lx + i), r.u1[0][i], L.up_barU);
-                st_async_f32(L.up_u2D + 4u * (4 * lx + i), r.u2[0][i], L.up_barU);
+                st_async_f32(g + OFF_U1D + 4u * (4 * lx + i), r.u1[0][i], b);
+                st_async_f32(g + OFF_U2D + 4u * (4 * lx + i), r.u2[0][i], b);
             }
         }
     };
@@ -737,14 +763,14 @@ __device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, Cluster
                 l11[j] = __shfl_up_sync(0xffffffffu, r.p11[j][3], 1, 16);
                 l21[j] = __shfl_up_sync(0xffffffffu, r.p21[j][3], 1, 16);
             }
-            if (wait_p) {
-                mbar_wait_cluster(barP, parP);
+            if (role & CR_WAIT_P) {
+                mbar_wait_addr(barP_a, parP);
                 parP ^= 1;
-                if (L.has_left && lx == 0) {
+                if (role & CR_LEFT) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) { l11[j] = gh->p11L[2 * tr + j]; l21[j] = gh->p21L[2 * tr + j]; }
                 }
-                if (L.has_up && tr == 0) {
+                if (role & CR_UP) {
                     ld4(gh->p12U + 4 * lx, up12);
                     ld4(gh->p22U + 4 * lx, up22);
                 }
@@ -772,7 +798,7 @@ __device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, Cluster
         st4(ex_u1 + mine, r.u1[0]);
         st4(ex_u2 + mine, r.u2[0]);
         __syncthreads();
-        if (wait_p && threadIdx.x == 0) mbar_expect_tx(barP, bytes_p);  // every thread is past this phase's wait: re-arm
+        if ((role & (CR_WAIT_P | CR_ARM)) == (CR_WAIT_P | CR_ARM)) mbar_expect_tx_addr(barP_a, bytes_p);  // re-arm
 
         // ---------------- dual update (estimateDualVariables) ----------------
         {
@@ -784,14 +810,14 @@ __device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, Cluster
                 r1[j] = __shfl_down_sync(0xffffffffu, r.u1[j][0], 1, 16);
                 r2[j] = __shfl_down_sync(0xffffffffu, r.u2[j][0], 1, 16);
             }
-            if (wait_u) {
-                mbar_wait_cluster(barU, parU);
+            if (role & CR_WAIT_U) {
+                mbar_wait_addr(barU_a, parU);
                 parU ^= 1;
-                if (L.has_right && lx == 15) {
+                if (role & CR_RIGHT) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) { r1[j] = gh->u1R[2 * tr + j]; r2[j] = gh->u2R[2 * tr + j]; }
                 }
-                if (L.has_down && tr == 31) {
+                if (role & CR_DOWN) {
                     ld4(gh->u1D + 4 * lx, dn1);
                     ld4(gh->u2D + 4 * lx, dn2);
                 }
@@ -818,7 +844,7 @@ __device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, Cluster
         st4(ex_p12 + mine, r.p12[1]);
         st4(ex_p22 + mine, r.p22[1]);
         __syncthreads();
-        if (wait_u && threadIdx.x == 0) mbar_expect_tx(barU, bytes_u);
+        if ((role & (CR_WAIT_U | CR_ARM)) == (CR_WAIT_U | CR_ARM)) mbar_expect_tx_addr(barU_a, bytes_u);
     }
 }
 
@@ -845,22 +871,14 @@ __global__ void __launch_bounds__(NT, 1)
     const int qx = (int)rank % cluster_x, qy = (int)rank / cluster_x;
     const int cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
 
-    ClusterLinks L;
-    L.has_left = qx > 0; L.has_right = qx < cluster_x - 1; L.has_up = qy > 0; L.has_down = qy < cluster_y - 1;
-    {
-        const uint32_t rr = L.has_right ? rank + 1 : rank, rd = L.has_down ? rank + cluster_x : rank;
-        const uint32_t rl = L.has_left ? rank - 1 : rank, ru = L.has_up ? rank - cluster_x : rank;
-        L.right_p11L = cluster_map(smem_u32(gh->p11L), rr); L.right_p21L = cluster_map(smem_u32(gh->p21L), rr);
-        L.right_barP = cluster_map(smem_u32(barP), rr);
-        L.down_p12U = cluster_map(smem_u32(gh->p12U), rd); L.down_p22U = cluster_map(smem_u32(gh->p22U), rd);
-        L.down_barP = cluster_map(smem_u32(barP), rd);
-        L.left_u1R = cluster_map(smem_u32(gh->u1R), rl); L.left_u2R = cluster_map(smem_u32(gh->u2R), rl);
-        L.left_barU = cluster_map(smem_u32(barU), rl);
-        L.up_u1D = cluster_map(smem_u32(gh->u1D), ru); L.up_u2D = cluster_map(smem_u32(gh->u2D), ru);
-        L.up_barU = cluster_map(smem_u32(barU), ru);
-    }
-    const uint32_t bytes_p = (L.has_left ? 2u * R * 4u : 0u) + (L.has_up ? 2u * R * 4u : 0u);
-    const uint32_t bytes_u = (L.has_right ? 2u * R * 4u : 0u) + (L.has_down ? 2u * R * 4u : 0u);
+    const bool has_left = qx > 0, has_right = qx < cluster_x - 1, has_up = qy > 0, has_down = qy < cluster_y - 1;
+    const uint32_t role = (has_left && lx == 0 ? CR_LEFT : 0u) | (has_up && tr == 0 ? CR_UP : 0u) |
+                          (has_right && lx == 15 ? CR_RIGHT : 0u) | (has_down && tr == 31 ? CR_DOWN : 0u) |
+                          (has_left || has_up ? CR_WAIT_P : 0u) | (has_right || has_down ? CR_WAIT_U : 0u) |
+                          (tid == 0 ? CR_ARM : 0u);
+    const uint32_t gh_a = smem_u32(gh), barP_a = smem_u32(barP), barU_a = smem_u32(barU);
+    const uint32_t bytes_p = (has_left ? 2u * R * 4u : 0u) + (has_up ? 2u * R * 4u : 0u);
+    const uint32_t bytes_u = (has_right ? 2u * R * 4u : 0u) + (has_down ? 2u * R * 4u : 0u);
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -923,13 +941,15 @@ __global__ void __launch_bounds__(NT, 1)
         const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
         const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
         if (border)
-            tile_iterate_cluster<true>(r, ex, gh, L, barP, barU, parP, parU, iters, k, lx, tr, gxb, gyb, cols, rows);
+            tile_iterate_cluster<true>(r, ex, gh, gh_a, barP_a, barU_a, role, rank, (uint32_t)cluster_x, bytes_p, bytes_u,
+                                       parP, parU, iters, k, lx, tr, gxb, gyb, cols, rows);
         else
-            tile_iterate_cluster<false>(r, ex, gh, L, barP, barU, parP, parU, iters, k, lx, tr, gxb, gyb, cols, rows);
+            tile_iterate_cluster<false>(r, ex, gh, gh_a, barP_a, barU_a, role, rank, (uint32_t)cluster_x, bytes_p, bytes_u,
+                                        parP, parU, iters, k, lx, tr, gxb, gyb, cols, rows);
 
         // valid part of my region: the halo is only on the sides that are outer sides of the super-region
-        const int x_lo = L.has_left ? 0 : halo, x_hi = L.has_right ? R : R - halo;
-        const int y_lo = L.has_up ? 0 : halo, y_hi = L.has_down ? R : R - halo;
+        const int x_lo = has_left ? 0 : halo, x_hi = has_right ? R : R - halo;
+        const int y_lo = has_up ? 0 : halo, y_hi = has_down ? R : R - halo;
         const int rx = 4 * lx;
         if (rx >= x_lo && rx < x_hi && gxb >= 0 && gxb < cols) {
             const bool full = gxb + 3 < cols;
