@@ -271,16 +271,19 @@ def side_measurements(pairs, flow_views, dev, H, W):
     import opencv_contrib_b200 as ocb
     out = {}
 
+    side = torch.cuda.Stream()  # a real stream: the legacy default stream takes the no-graph, device-synchronising path
+
     def time_alg(alg, a, b, f, n):
+        torch.cuda.synchronize()
         for _ in range(2):
-            alg.calc(a, b, f)
-        torch.cuda.synchronize()
+            alg.calc(a, b, f, side)
+        side.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(side)
         for _ in range(n):
-            alg.calc(a, b, f)
-        e1.record()
-        torch.cuda.synchronize()
+            alg.calc(a, b, f, side)
+        e1.record(side)
+        side.synchronize()
         return 1000.0 * n / e0.elapsed_time(e1)
 
     a, b = pairs[0]
@@ -297,7 +300,8 @@ def side_measurements(pairs, flow_views, dev, H, W):
         alg = ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, 10, 77, 10)
         out["brox_720p_10_77_10_pairs_per_s_1stream"] = time_alg(alg, bx, by, bf, 3)
         alg.resetStats()
-        alg.calc(bx, by, bf)
+        alg.calc(bx, by, bf, side)
+        side.synchronize()
         out["brox_720p_launches_per_pair"] = alg.getStats()["launches"]
         out["denselk_1080p_default_pairs_per_s_1stream"] = time_alg(ocb.DensePyrLKOpticalFlow_create(), a, b, f, 3)
         # video front end (one upload per frame, 3-stream pipeline): host frames in, host flows out
