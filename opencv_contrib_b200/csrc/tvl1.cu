@@ -120,9 +120,6 @@ __global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p
     rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
 }
 
-#ifndef WARP_SEP_MIN_BLOCKS
-#define WARP_SEP_MIN_BLOCKS 6
-#endif
 // Border pixels of the warp (window touches the image edge): clamp every tap, then take the clamped-neighbour gradient
 // at the clamped tap (point / clamp texture semantics of tvl1flow.cu:106-164).  A real call on purpose.
 __device__ __noinline__ void warp_border_taps(const Plane I1, int rows, int cols, int ix, int iy, const float (&kx)[4],
@@ -156,14 +153,17 @@ __device__ __forceinline__ void keys_weights(float t, float (&k)[4]) {
     k[3] = (0.5f * t - 0.5f) * t * t;
 }
 
-// Separable form of the same warp (round 2, opt-in as aux_path 1): w_ij = kx[i] * ky[j], so the three weighted sums are row
+// Separable form of the same warp (round 2, the default): w_ij = kx[i] * ky[j], so the three weighted sums are row
 // sums r[j] = sum_i kx[i] W[j][i+1] (6 rows), rx[j] = sum_i kx[i] (W[j][i+2] - W[j][i]) (4 rows) combined with ky:
 //   I1w = sum_j ky[j] r[j+1],  I1wx = 0.5 sum_j ky[j] rx[j+1],  I1wy = 0.5 sum_j ky[j] (r[j+2] - r[j]),
-// about half the arithmetic of the tap-by-tap form (which handles the few pixels whose window touches the image border).
-// Results differ from the tap-by-tap accumulation by rounding only.  Measured on B200 (1080p 5x10x30): 1.24 ms per
-// pair against 1.26 ms -- the kernel is bound by its 36-texel gather, not by arithmetic -- so the reference-ordered
-// kernel stays the default.
-__global__ void __launch_bounds__(256, WARP_SEP_MIN_BLOCKS) k_tvl1_warp_sep(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
+// about half the arithmetic of the tap-by-tap form (kept as aux_path 1; the few pixels whose window touches the image
+// border take its loop through an out-of-line call).  Results differ from the tap-by-tap accumulation by rounding only.
+// The warp kernel is bound by dependent memory round trips (flow -> window -> stores; ncu: long_scoreboard 5.3 stalls per
+// issue at 42 % of the warp slots), not by arithmetic: the separable form at 62 registers measured no faster (1.24 vs
+// 1.26 ms per 1080p pair); what it buys is registers -- row by row it never holds the 6x6 window, fits 40 registers
+// and runs 6 blocks per SM instead of 4: 1.22 vs 1.43 ms per pair.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_tvl1_warp_sep(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
                                                        Plane grad, Plane rho, int rows, int cols) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -776,12 +776,15 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
 
     for (int w = 0; w < P.warps; ++w) {
         point_T_at(cur);
-        if (knobs.aux_path == 1)  // separable form: half the arithmetic, measured no faster (the kernel is gather-bound)
-            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_sep, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx,
-                       T.I1wy, T.grad, T.rho_c, rows, cols);
-        else  // tap-by-tap accumulation in the reference's order
+        if (knobs.aux_path == 1)  // tap-by-tap accumulation in the reference's order (62 registers, 4 blocks / SM)
             B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy,
                        T.grad, T.rho_c, rows, cols);
+        else if (knobs.aux_path == 2)  // separable form at 32 registers (8 blocks / SM)
+            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_sep<8>, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx,
+                       T.I1wy, T.grad, T.rho_c, rows, cols);
+        else  // separable form at 40 registers (6 blocks / SM): the default
+            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_sep<6>, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx,
+                       T.I1wy, T.grad, T.rho_c, rows, cols);
 
         if (blocked_ok && !(P.epsilon > 0.0)) {  // fixed schedule
             if (med_k == 1) {
