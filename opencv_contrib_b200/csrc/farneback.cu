@@ -539,7 +539,7 @@ __device__ __forceinline__ float box_first(const float (&v)[M]) {
 
 constexpr int FT_W = 64, FT_H = 32;
 
-template <int K, bool GAUSS, bool QUAD, int NT = 256, int MINB = 1>
+template <int K, bool GAUSS, bool QUAD, int NT = 256, int MINB = (NT == 256 ? 2 : 1)>
 __global__ void __launch_bounds__(NT, MINB) k_farn_iter_fast(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
                                                         Plane flowy, int rows, int cols, float box_inv,
                                                         const float *__restrict__ g, int update_matrices,
