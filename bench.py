@@ -533,8 +533,21 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         if args.gather == "native":
+            # the gather is not part of the compute path: if the library cannot create its communicator on this box
+            # (no libnccl.so.2 to dlopen, id exchange failed) the run goes on with torch.distributed.gather and says so
             from opencv_contrib_b200.batch import NativeComm
-            NATIVE_COMM["comm"] = NativeComm.from_torch_distributed()
+            ok = torch.ones(1, device=dev)
+            try:
+                NATIVE_COMM["comm"] = NativeComm.from_torch_distributed()
+            except Exception as e:  # noqa: BLE001
+                NATIVE_COMM["error"] = repr(e)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks take the same path
+            if float(ok.item()) == 0.0:
+                NATIVE_COMM.pop("comm", None)
+                if rank == 0:
+                    print("native NCCL gather unavailable (%s): using torch.distributed.gather" % NATIVE_COMM.get("error", "another rank failed"),
+                          file=sys.stderr, flush=True)
 
     head = args.workload or "tvl1"
     sampler = ClockSampler(local_rank) if rank == 0 else None

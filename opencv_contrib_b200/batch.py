@@ -217,12 +217,26 @@ class NativeComm:
     @classmethod
     def from_torch_distributed(cls, group=None):
         """Bootstrap over an initialised torch.distributed process group (any backend): rank 0 creates the NCCL id
-        and broadcasts its 128 bytes; every rank then joins on its CURRENT CUDA device."""
+        and broadcasts its 128 bytes; every rank then joins on its CURRENT CUDA device.  Failures before the collective
+        ncclCommInitRank are agreed on by all ranks first, so nobody is left waiting in it."""
         import torch.distributed as dist
+        from . import _lib
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        box = [cls.unique_id() if rank == 0 and world > 1 else b""]
-        if world > 1:
-            dist.broadcast_object_list(box, src=0, group=group)
+        if world == 1:
+            return cls(b"", 0, 1)
+        avail = [None] * world
+        dist.all_gather_object(avail, int(_lib.lib().b2f_comm_available()), group=group)
+        if not all(avail):
+            raise RuntimeError("libnccl.so.2 cannot be loaded on rank(s) %s" % [r for r, a in enumerate(avail) if not a])
+        box = [b""]
+        if rank == 0:
+            try:
+                box = [cls.unique_id()]
+            except Exception:  # noqa: BLE001 -- reported below, on every rank
+                box = [b""]
+        dist.broadcast_object_list(box, src=0, group=group)
+        if len(box[0]) != 128:
+            raise RuntimeError("rank 0 could not create an NCCL unique id")
         return cls(box[0], rank, world)
 
     def close(self):
