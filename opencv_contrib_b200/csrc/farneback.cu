@@ -1239,18 +1239,20 @@ void FarnebackEngine::solve(Ctx &c) {
                 else if (quad && wide_blocks)
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 512>), gf, dim3(512), smem_fast, Ma, Mb,
                                R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
-                else if (quad && knobs.aux_path == 2)  // unconstrained: 128 registers, 2 blocks / SM (round 1)
-                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true>), gf, dim3(256), smem_fast, Ma, Mb, R0,
-                               R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else if (quad && knobs.aux_path == 3)  // 80 registers: 3 blocks / SM
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 256, 3>), gf, dim3(256), smem_fast, Ma, Mb,
+                               R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
                 else if (quad && knobs.aux_path == 4)  // 64 registers: 4 blocks / SM
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 256, 4>), gf, dim3(256), smem_fast, Ma, Mb,
                                R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
                 else if (quad)
-                    // the kernel waits on its gathers (ncu: long_scoreboard 5.3 per issue, 22 % of the warp slots at 128
-                    // registers): capped at 80 registers it keeps 3 blocks per SM resident -- 1080p pair 1.585 -> 1.426 ms
-                    // single stream, same bits (40 bytes of spill)
-                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 256, 3>), gf, dim3(256), smem_fast, Ma, Mb,
-                               R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                    // 128 registers, 2 blocks / SM.  The kernel waits on its gathers (ncu: long_scoreboard 5.3 per issue at
+                    // 22 % of the warp slots), but more resident blocks do not pay: capped at 80 registers (3 blocks) a 1080p
+                    // pair takes 1.393 vs 1.364 ms single stream and 0.949 vs 0.942 ms on 8 streams, at 64 registers
+                    // (4 blocks) 1.487 / 0.989 ms -- the spills and the lost instruction-level parallelism cost what the
+                    // occupancy gains (aux_path 3 / 4 keep the variants, bit-identical)
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true>), gf, dim3(256), smem_fast, Ma, Mb, R0,
+                               R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
                 else
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, false>), gf, dim3(256), smem_fast, Ma, Mb,
                                R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);

@@ -746,6 +746,8 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
             const int kk = tvl1_blocked_pick_k(knobs.fused_iters, count - done, rows, cols);
             if (use_tma && knobs.kernel_path == 5)  // packed-FP32 variant: measured 8 % slower than the scalar kernel
                 tvl1_packed_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
+            else if (use_tma && knobs.kernel_path == 8)  // two warp groups half an iteration apart
+                tvl1_tma2g_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
             else if (use_tma && (knobs.kernel_path == 6 || knobs.kernel_path == 7))  // 2x2 / 2x1 thread-block clusters
                 tvl1_cluster_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, 2,
                                     knobs.kernel_path == 6 ? 2 : 1);

@@ -109,6 +109,124 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-group variant of tile_iterate (round 2, kernel_path 8).  ncu shows the two half iterations in different regimes:
+// the primal update is FP32-issue bound, the dual update SFU / MIO-queue bound, and the CTA-wide barriers put all 16
+// warps into the same regime at the same time.  Here the upper half of the region (warps 0-7, group A) runs half an
+// iteration AHEAD of the lower half (warps 8-15, group B): while A's warps queue on the SFU in their dual update, B's
+// warps fill the FP32 issue slots with their primal update, and vice versa.
+//   * each group synchronises internally with its own named barrier (bar.sync 1 / 2, 256 threads);
+//   * B may start primal(it) only when A has finished primal(it) (A: bar.arrive 3, B: bar.sync 3) -- this is what keeps
+//     the groups half an iteration apart; A never waits for B in its primal update (up-neighbours only);
+//   * the seam rows cross between warp 7 and warp 8 only: warp 8 publishes its first row of u right after computing it
+//     and arrives on barrier 4, warp 7 syncs on it before it touches its last row in the dual update; warp 7 arrives on
+//     barrier 5 after publishing its last row of p, warp 8 syncs on it before its next primal update;
+//   * the exchange arrays are double-buffered by iteration parity, so a group that runs ahead never overwrites a row
+//     the other group still has to read.
+// Same arithmetic per pixel, same operands: bit-identical to tile_iterate.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <bool BORDER>
+__device__ __forceinline__ void tile_iterate_2g(Regs &r, float *ex, int iters, const Tvl1Scalars k, int lx, int tr, int gxb,
+                                                int gyb, int W, int H) {
+    // ex: [parity][u1 | u2 | p12 | p22][32 thread rows][64]
+    const int mine = tr * R + 4 * lx;
+    const int up = max(tr - 1, 0) * R + 4 * lx;
+    const int dn = min(tr + 1, 31) * R + 4 * lx;
+    const int grp = tr >> 4;             // 0 = A (rows 0..31), 1 = B (rows 32..63)
+    const int warp = tr >> 1;            // 0..15
+    const int gbar = 1 + grp;
+
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
+
+    st4(ex + 2 * EX_F + mine, r.p12[1]);   // parity 0
+    st4(ex + 3 * EX_F + mine, r.p22[1]);
+    __syncthreads();
+
+    for (int it = 0; it < iters; ++it) {
+        float *exr = ex + (it & 1) * 4 * EX_F;        // u rows of this iteration / p rows read by this primal update
+        float *exw = ex + ((it + 1) & 1) * 4 * EX_F;  // p rows written by this dual update
+        if (grp == 1) named_sync(3, NT);              // B: not before A has finished primal(it)
+        // ---------------- primal update (estimateU) ----------------
+        if (warp == 8 && it > 0) named_sync(5, 64);   // A's last row of p (dual update it-1) is published
+        float up12[4], up22[4];
+        ld4(exr + 2 * EX_F + up, up12);
+        ld4(exr + 3 * EX_F + up, up22);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float l11 = __shfl_up_sync(0xffffffffu, r.p11[j][3], 1, 16);
+            const float l21 = __shfl_up_sync(0xffffffffu, r.p21[j][3], 1, 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float pl11 = i ? r.p11[j][i ? i - 1 : 0] : l11;
+                float pl21 = i ? r.p21[j][i ? i - 1 : 0] : l21;
+                float pu12 = j ? r.p12[0][i] : up12[i];
+                float pu22 = j ? r.p22[0][i] : up22[i];
+                if (BORDER) {
+                    if (gxb + i == 0) { pl11 = 0.f; pl21 = 0.f; }
+                    if (gyb + j == 0) { pu12 = 0.f; pu22 = 0.f; }
+                }
+                float a, b;
+                tvl1_update_u(k, r.Ix[j][i], r.Iy[j][i], r.gr[j][i], r.rc[j][i], r.u1[j][i], r.u2[j][i], r.p11[j][i], pl11,
+                              r.p12[j][i], pu12, r.p21[j][i], pl21, r.p22[j][i], pu22, a, b);
+                r.u1[j][i] = a;
+                r.u2[j][i] = b;
+            }
+            if (j == 0) {  // the top row is what the thread row above needs: publish it as soon as it exists
+                st4(exr + mine, r.u1[0]);
+                st4(exr + EX_F + mine, r.u2[0]);
+                if (warp == 8) {
+                    __syncwarp();
+                    named_arrive(4, 64);  // B's first row of u is there for A's warp 7
+                }
+            }
+        }
+        if (grp == 0) named_arrive(3, NT);  // A has finished primal(it): B may start its own
+        named_sync(gbar, NT / 2);
+
+        // ---------------- dual update (estimateDualVariables) ----------------
+        float dn1[4], dn2[4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j == 1) {  // the row below is only needed now; warp 7 takes it from group B, which runs half an iteration behind
+                if (warp == 7) named_sync(4, 64);
+                ld4(exr + dn, dn1);
+                ld4(exr + EX_F + dn, dn2);
+            }
+            const float r1 = __shfl_down_sync(0xffffffffu, r.u1[j][0], 1, 16);
+            const float r2 = __shfl_down_sync(0xffffffffu, r.u2[j][0], 1, 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float c1 = r.u1[j][i], c2 = r.u2[j][i];
+                const float ur1 = i < 3 ? r.u1[j][i < 3 ? i + 1 : 3] : r1;
+                const float ur2 = i < 3 ? r.u2[j][i < 3 ? i + 1 : 3] : r2;
+                const float ud1 = j == 0 ? r.u1[1][i] : dn1[i];
+                const float ud2 = j == 0 ? r.u2[1][i] : dn2[i];
+                float ux1 = __fsub_rn(ur1, c1), uy1 = __fsub_rn(ud1, c1);
+                float ux2 = __fsub_rn(ur2, c2), uy2 = __fsub_rn(ud2, c2);
+                if (BORDER) {
+                    if (gxb + i == W - 1) { ux1 = 0.f; ux2 = 0.f; }
+                    if (gyb + j == H - 1) { uy1 = 0.f; uy2 = 0.f; }
+                }
+                tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, r.p11[j][i], r.p12[j][i], r.p21[j][i], r.p22[j][i]);
+            }
+        }
+        st4(exw + 2 * EX_F + mine, r.p12[1]);
+        st4(exw + 3 * EX_F + mine, r.p22[1]);
+        if (warp == 7 && it + 1 < iters) {
+            __syncwarp();
+            named_arrive(5, 64);  // A's last row of p is there for B's warp 8
+        }
+        named_sync(gbar, NT / 2);
+    }
+    __syncthreads();  // both groups are done with the tile (B half an iteration later)
+}
+
 struct InPlanes {
     Plane p[N_IN];
 };
@@ -263,7 +381,7 @@ __device__ __forceinline__ void store_pairs(float *p, const float (&v)[4], int m
     else if (m1 == 1) p[2] = v[2];
 }
 
-template <bool ELECT, int TBOX_W>
+template <bool ELECT, int TBOX_W, bool TWOG = false>
 __global__ void __launch_bounds__(NT, 1)
     k_tvl1_blocked_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12,
                        Plane o_p21, Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int tile,
@@ -276,7 +394,7 @@ __global__ void __launch_bounds__(NT, 1)
     extern __shared__ __align__(1024) float smem[];
     float *stage = smem;
     float *ex = smem + N_IN * TPLANE_F;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(ex + 4 * EX_F);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ex + (TWOG ? 8 : 4) * EX_F);  // two-group variant: exchange double-buffered
 
     const int tid = threadIdx.x;
     const int lx = tid & 15, tr = tid >> 4;
@@ -343,7 +461,12 @@ __global__ void __launch_bounds__(NT, 1)
 
         const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
         const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
-        if (border)
+        if (TWOG) {
+            if (border)
+                tile_iterate_2g<true>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
+            else
+                tile_iterate_2g<false>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
+        } else if (border)
             tile_iterate<true>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
         else
             tile_iterate<false>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
@@ -1062,6 +1185,21 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
                    halo, tile, tiles_x, ntiles, nullptr);
 }
 
+// Two-group (anti-phase) variant of the aligned kernel; halo rounded up to a multiple of 4 like the packed kernel.
+void tvl1_tma2g_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                       const Tvl1Scalars &k, int iters, int num_sms) {
+    const Tvl1State &so = B.s[cur ^ 1];
+    const int halo = (iters + 3) & ~3;
+    const int tile = R - 2 * halo;
+    const int tiles_x = div_up(cols, tile), tiles_y = div_up(rows, tile);
+    const int ntiles = tiles_x * tiles_y;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    const double bytes = 64.0 * (double)rows * cols * iters;
+    const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;
+    B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R, true>), dim3(grid), dim3(NT), smem_tma_bytes(R) + sizeof(float) * 4 * EX_F,
+               *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr);
+}
+
 // One pass whose iteration count (0..8; negative = skip the pass) is read from device memory at run time: fixed
 // geometry (8-pixel halo, 48-pixel tiles, 64-wide boxes) so the launch can sit in a CUDA graph's while-loop body.
 void tvl1_tma_launch_dev(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
@@ -1169,6 +1307,9 @@ cudaError_t tvl1_blocked_init() {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_tma_bytes(R));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(smem_tma_bytes(R) + sizeof(float) * 4 * EX_F));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_tvl1_packed_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_packed_bytes());

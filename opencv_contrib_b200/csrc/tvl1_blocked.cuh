@@ -55,6 +55,10 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
 void tvl1_tma_launch_dev(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                          const Tvl1Scalars &k, const int *iters_dev, int num_sms);
 
+// Two-group variant: the two halves of the region run half an iteration apart (FP32-bound primal against SFU-bound dual).
+void tvl1_tma2g_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                       const Tvl1Scalars &k, int iters, int num_sms);
+
 // Packed-FP32 (f32x2) persistent TMA kernel, the default path; iters <= TVL1_KMAX.
 void tvl1_packed_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                         const Tvl1Scalars &k, int iters, int num_sms);

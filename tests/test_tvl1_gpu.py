@@ -61,7 +61,8 @@ def test_blocked_kernel_bit_identical_to_unfused(cuda_device, K):
     # 0 = scalar persistent TMA kernel, 5 = packed-FP32 (f32x2) variant, 6 / 7 = 2x2 / 2x1 thread-block clusters with
     # DSMEM ghost exchange, 2 = blocked kernel with plain loads
     import os
-    paths = (0, 5, 2) if os.environ.get("B2F_SKIP_CLUSTER") else (0, 5, 6, 7, 2)
+    # 8 = two warp groups half an iteration apart (named barriers)
+    paths = (0, 5, 2) if os.environ.get("B2F_SKIP_CLUSTER") else (0, 5, 6, 7, 8, 2)
     for path in paths:
         for graph in (0, 1):
             b, _ = _run(cuda_device, I0, I1, path=path, fused=K, graph=graph, **kw)

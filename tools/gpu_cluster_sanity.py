@@ -11,7 +11,7 @@ for (h, w) in [(203, 277), (540, 960)]:
     I0, I1, _ = synth.make_pair(h, w, seed=3, kind="smooth")
     d0, d1 = torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev)
     outs = {}
-    for path in (0, 6, 7):
+    for path in (0, 6, 7, 8):
         for K in (8, 3):
             alg = ocb.OpticalFlowDual_TVL1_create(nscales=3, warps=2, epsilon=0.0, iterations=23)
             alg.setEngineOption("kernel_path", path)

@@ -10,7 +10,7 @@ I0, I1, gt = synth.make_pair(1080, 1920, seed=0, kind="smooth")
 d0, d1 = torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev)
 ref = None
 NS = 8
-for aux in [int(a) for a in (sys.argv[1:] or ["0", "2", "4"])]:
+for aux in [int(a) for a in (sys.argv[1:] or ["0", "3", "4"])]:
     algs = [ocb.FarnebackOpticalFlow_create() for _ in range(NS)]
     for a in algs: a.setEngineOption("aux_path", aux)
     flows = [torch.empty((1080, 1920, 2), dtype=torch.float32, device=dev) for _ in range(NS)]
