@@ -17,6 +17,7 @@
 #include <new>
 #include <vector>
 
+#include <climits>
 #include "common.cuh"
 
 struct b2f_batch;
@@ -32,6 +33,7 @@ struct NcclApi {
     void *lib = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, void *) = nullptr;  // optional (>= 2.14)
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
     ncclResult_t (*CommUserRank)(const ncclComm_t, int *) = nullptr;
@@ -54,6 +56,7 @@ NcclApi *nccl_api() {
 #define B2F_SYM(field, name) *reinterpret_cast<void **>(&api.field) = dlsym(h, name)
     B2F_SYM(GetUniqueId, "ncclGetUniqueId");
     B2F_SYM(CommInitRank, "ncclCommInitRank");
+    B2F_SYM(CommInitRankConfig, "ncclCommInitRankConfig");
     B2F_SYM(CommDestroy, "ncclCommDestroy");
     B2F_SYM(CommCount, "ncclCommCount");
     B2F_SYM(CommUserRank, "ncclCommUserRank");
@@ -108,8 +111,15 @@ int comm_enqueue_pair(b2f_comm *c, int i, int n_pairs, cudaStream_t es, const b2
         if (!nccl_ok(c->api->Send(flow_i->data, count, ncclFloat, dst, c->comm, c->stream))) return B2F_CUDA_ERROR;
         return B2F_OK;
     }
-    // root: the receives of pair i from every other rank do not depend on the local solve
+    // root: the receives of pair i do not depend on the local solve, but they are ordered behind it all the same.
+    // An NCCL receive is a kernel that spins on an SM until its peer sends; posted at batch start it would hold
+    // that SM for the whole batch.  Behind the root's own pair i it starts about when the peers (which run in
+    // lock step) start sending theirs.
     if (!gathered) return B2F_BAD_ARG;
+    if (cudaEventRecord(c->pair_done[i], es) != cudaSuccess || cudaStreamWaitEvent(c->stream, c->pair_done[i], 0) != cudaSuccess) {
+        cudaGetLastError();
+        return B2F_CUDA_ERROR;
+    }
     if (!nccl_ok(c->api->GroupStart())) return B2F_CUDA_ERROR;
     bool ok = true;
     for (int r = 0; r < c->nranks && ok; ++r) {
@@ -175,7 +185,11 @@ int b2f_comm_unique_id(void *id, size_t bytes) {
 }
 
 static int finish_create(b2f_comm *c, b2f_comm **out) {
-    if (cudaGetDevice(&c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // highest priority: a transfer's CTA is placed as soon as any solver CTA retires
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaGetDevice(&c->device) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         b2f_comm_destroy(c);
@@ -199,7 +213,20 @@ int b2f_comm_create(const void *id, size_t bytes, int rank, int nranks, b2f_comm
         ncclUniqueId u;
         std::memcpy(&u, id, sizeof(u));
         c->api = api;
-        const ncclResult_t r = api->CommInitRank(&c->comm, nranks, u, rank);  // collective: every rank calls it
+        // A flow is 16.6 MB and a rank produces ~130 of them a second: one channel per pair of ranks is plenty
+        // (four when the root takes in seven peers), and every further NCCL CTA would sit on an SM the solvers
+        // want (measured at N=2: default channels 245.5 pairs/s, one channel 263.1).  The config layout is NCCL 2.17's; newer libraries
+        // accept it by its size/version fields.
+        struct CommConfig217 {
+            size_t size;
+            unsigned magic, version;
+            int blocking, cga_cluster_size, min_ctas, max_ctas;
+            const char *net_name;
+            int split_share;
+        } cfg = {sizeof(CommConfig217), 0xcafebeefu, 21700u, INT_MIN, INT_MIN, 1, nranks <= 2 ? 1 : 4, nullptr, INT_MIN};
+        ncclResult_t r = ncclInvalidUsage;
+        if (api->CommInitRankConfig) r = api->CommInitRankConfig(&c->comm, nranks, u, rank, &cfg);
+        if (r != ncclSuccess) r = api->CommInitRank(&c->comm, nranks, u, rank);  // collective: every rank calls it
         if (r != ncclSuccess) {
             c->last_nccl_error = (int)r;
             delete c;
