@@ -161,14 +161,17 @@ typedef enum b2f_param_id {
     /* engine knobs (no reference counterpart) */
     B2F_ENGINE_FUSED_ITERS = 900, /* TV-L1: inner iterations fused per HBM pass (0 = auto)     */
     B2F_ENGINE_USE_GRAPH = 901,   /* capture the fixed schedule in a CUDA graph (default 1)    */
-    B2F_ENGINE_KERNEL_PATH = 902, /* TV-L1: 0 = auto (persistent TMA kernel), 1 = unfused reference-shaped
-                                     kernels, 2 = blocked kernel without TMA, 3 = TMA kernel without
-                                     elect.sync, 5 = packed-FP32 (f32x2) TMA kernel, 6 / 7 = 2x2 / 2x1-cluster kernels,
-                                     8 = two warp groups half an iteration apart */
+    B2F_ENGINE_KERNEL_PATH = 902, /* TV-L1: 0 = auto (persistent TMA kernel, centre tiles stored by TMA), 1 = unfused
+                                     reference-shaped kernels, 2 = blocked kernel without TMA, 3 = TMA kernel without
+                                     elect.sync, 4 = TMA loads with the round-1 STG epilogue, 5 = packed-FP32 (f32x2)
+                                     TMA kernel, 6 / 7 = 2x2 / 2x1-cluster kernels, 8 = two warp groups half an
+                                     iteration apart, 9 = warps synchronise with their neighbours through mbarriers
+                                     (11 = 9 with the TMA-store epilogue).  All bit-identical; 0 is the fastest.   */
     B2F_ENGINE_AUX_PATH = 903     /* variant of the secondary kernels.  TV-L1: 0 = separable warp kernel (40
                                      registers), 1 = tap-by-tap warp kernel (accumulation in the reference's
                                      order), 2 = separable at 32 registers.  Farneback: fused iteration kernel
-                                     at 0 = 128 registers (2 blocks / SM), 3 = 80, 4 = 64 registers          */
+                                     at 0 = 128 registers (2 blocks / SM), 3 = 80, 4 = 64 registers, 5 = R1 gather
+                                     with lanes on consecutive pixels (measured slower)                      */
 } b2f_param_id;
 
 /* cv::medianBlur for CV_32FC1, ksize 3 or 5, replicated border, not in place: the primitive behind

@@ -428,6 +428,88 @@ __device__ __forceinline__ void farn_update_matrices_quad(const Stack5 &R0, cons
     }
 }
 
+
+// updateMatrices for 4 pixels at arbitrary positions (xs[e], ys[e]); used by the lane-transposed gather of
+// k_farn_iter_fast, where lane L of a warp owns pixels L, L+32 of two tile rows: one gather instruction of the warp
+// then covers 32 CONSECUTIVE pixels (4-6 sectors) instead of every fourth pixel of 128 (16 sectors, a quarter of each
+// used).  Same arithmetic per pixel as farn_update_matrices_px / _quad; ok[e] = pixel inside the image.
+__device__ __forceinline__ void farn_update_matrices_spread(const Stack5 &R0, const Stack5 &R1, int rows, int cols,
+                                                            const int (&xs)[4], const int (&ys)[4], const bool (&ok)[4],
+                                                            const float (&dx)[4], const float (&dy)[4],
+                                                            float (&m)[4][5]) {
+    float a00[4], a01[4], a10[4], a11[4];
+    const float *base[4];
+    bool inb[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float fx = xs[e] + dx[e], fy = ys[e] + dy[e];
+        const float ffx = fminf(fmaxf(floorf(fx), -4.f), (float)cols + 4.f);
+        const float ffy = fminf(fmaxf(floorf(fy), -4.f), (float)rows + 4.f);
+        const int x1 = (int)ffx, y1 = (int)ffy;
+        fx -= floorf(fx);
+        fy -= floorf(fy);
+        inb[e] = x1 >= 0 && y1 >= 0 && x1 < cols - 1 && y1 < rows - 1 && ok[e];
+        a00[e] = (1.f - fx) * (1.f - fy);
+        a01[e] = fx * (1.f - fy);
+        a10[e] = (1.f - fx) * fy;
+        a11[e] = fx * fy;
+        base[e] = &R1.at(0, inb[e] ? y1 : 0, inb[e] ? x1 : 0);
+    }
+    const size_t ps = (size_t)R1.h * R1.pitch;
+    const int pitch = R1.pitch;
+    float g[5][4];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float t00[4], t01[4], t10[4], t11[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float *p = base[e];
+            const float *p2 = p + pitch;
+            t00[e] = __ldg(p);
+            t01[e] = __ldg(p + 1);
+            t10[e] = __ldg(p2);
+            t11[e] = __ldg(p2 + 1);
+            base[e] = p + ps;  // next plane
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g[k][e] = a00[e] * t00[e] + a01[e] * t01[e] + a10[e] * t10[e] + a11[e] * t11[e];
+    }
+    float r0v[5][4];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r0v[k][e] = ok[e] ? __ldg(&R0.at(k, ys[e], xs[e])) : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float r2, r3, r4, r5, r6;
+        if (inb[e]) {
+            r2 = g[0][e];
+            r3 = g[1][e];
+            r4 = (r0v[2][e] + g[2][e]) * 0.5f;
+            r5 = (r0v[3][e] + g[3][e]) * 0.5f;
+            r6 = (r0v[4][e] + g[4][e]) * 0.25f;
+        } else {
+            r2 = r3 = 0.f;
+            r4 = r0v[2][e];
+            r5 = r0v[3][e];
+            r6 = r0v[4][e] * 0.5f;
+        }
+        r2 = (r0v[0][e] - r2) * 0.5f;
+        r3 = (r0v[1][e] - r3) * 0.5f;
+        r2 += r4 * dy[e] + r6 * dx[e];
+        r3 += r6 * dy[e] + r5 * dx[e];
+        const int xe = xs[e], ye = ys[e];
+        const float scale = farn_border_w(min(xe, BORDER_SIZE)) * farn_border_w(min(ye, BORDER_SIZE)) *
+                            farn_border_w(min(cols - xe - 1, BORDER_SIZE)) * farn_border_w(min(rows - ye - 1, BORDER_SIZE));
+        r2 *= scale; r3 *= scale; r4 *= scale; r5 *= scale; r6 *= scale;
+        m[e][0] = r4 * r4 + r6 * r6;
+        m[e][1] = (r4 + r5) * r6;
+        m[e][2] = r5 * r5 + r6 * r6;
+        m[e][3] = r4 * r2 + r6 * r3;
+        m[e][4] = r6 * r2 + r5 * r3;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_farn_update_matrices(Plane flowx, Plane flowy, Stack5 R0, Stack5 R1, Stack5 M,
                                                               int rows, int cols) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -539,7 +621,7 @@ __device__ __forceinline__ float box_first(const float (&v)[M]) {
 
 constexpr int FT_W = 64, FT_H = 32;
 
-template <int K, bool GAUSS, bool QUAD, int NT = 256, int MINB = (NT == 256 ? 2 : 1)>
+template <int K, bool GAUSS, bool QUAD, int NT = 256, int MINB = (NT == 256 ? 2 : 1), bool XPOSE = false>
 __global__ void __launch_bounds__(NT, MINB) k_farn_iter_fast(Stack5 Min, Stack5 Mout, Stack5 R0, Stack5 R1, Plane flowx,
                                                         Plane flowy, int rows, int cols, float box_inv,
                                                         const float *__restrict__ g, int update_matrices,
@@ -604,7 +686,8 @@ __global__ void __launch_bounds__(NT, MINB) k_farn_iter_fast(Stack5 Min, Stack5 
     for (int task = tid; task < FT_H * (FT_W / 4); task += NT) {
         const int r = task / (FT_W / 4), q = task - r * (FT_W / 4);
         const int y = y0 + r, x = x0 + 4 * q;
-        if (y >= rows || x >= cols) continue;
+        const bool live = y < rows && x < cols;
+        if (!XPOSE && !live) continue;  // the transposed gather below needs the whole warp
         float res[5][4];
 #pragma unroll
         for (int pl = 0; pl < 5; ++pl) {
@@ -645,7 +728,7 @@ __global__ void __launch_bounds__(NT, MINB) k_farn_iter_fast(Stack5 Min, Stack5 
             fy[e] = (g22 * h1 - g12 * h2) * detInv;
         }
         const bool full = x + 3 < cols;
-        if (write_flow) {
+        if (write_flow && live) {
             if (full) {
                 *reinterpret_cast<float4 *>(&flowx.at(y, x)) = make_float4(fx[0], fx[1], fx[2], fx[3]);
                 *reinterpret_cast<float4 *>(&flowy.at(y, x)) = make_float4(fy[0], fy[1], fy[2], fy[3]);
@@ -656,7 +739,36 @@ __global__ void __launch_bounds__(NT, MINB) k_farn_iter_fast(Stack5 Min, Stack5 
                 }
             }
         }
-        if (update_matrices) {
+        if (XPOSE && update_matrices) {
+            // hand the displacements over to the lane-transposed mapping: the warp's two tile rows (2 x 64 pixels) go
+            // through a 1 KB buffer; lane L then owns columns L and L + 32 of both rows
+            const int lane = tid & 31;
+            float *tb = sm + 5 * FT_H * SW + (tid >> 5) * 256;  // [fx | fy][2 rows][64]
+            __syncwarp();
+            *reinterpret_cast<float4 *>(tb + (lane >> 4) * FT_W + 4 * (lane & 15)) = make_float4(fx[0], fx[1], fx[2], fx[3]);
+            *reinterpret_cast<float4 *>(tb + 128 + (lane >> 4) * FT_W + 4 * (lane & 15)) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+            __syncwarp();
+            const int rw = (task - lane) / (FT_W / 4);  // first of the warp's two rows
+            int xs[4], ys[4];
+            bool ok[4];
+            float dxs[4], dys[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int rr = e >> 1, cc = lane + 32 * (e & 1);
+                xs[e] = x0 + cc;
+                ys[e] = y0 + rw + rr;
+                ok[e] = xs[e] < cols && ys[e] < rows;
+                dxs[e] = tb[rr * FT_W + cc];
+                dys[e] = tb[128 + rr * FT_W + cc];
+            }
+            float m[4][5];
+            farn_update_matrices_spread(R0, R1, rows, cols, xs, ys, ok, dxs, dys, m);
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (ok[e]) Mout.at(pl, ys[e], xs[e]) = m[e][pl];
+        } else if (update_matrices) {
             float m[4][5];
             if (QUAD) {
                 farn_update_matrices_quad(R0, R1, rows, cols, x, y, fx, fy, m);
@@ -1082,6 +1194,7 @@ int FarnebackEngine::calc(const b2f_image *I0, const b2f_image *I1, b2f_image *f
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            c.check(cudaFuncSetAttribute(k_farn_iter_fast<6, false, true, 256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 8 * 1024));
             c.check(cudaFuncSetAttribute(k_farn_iter_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FARN_TMA_SMEM));
             c.check(cudaFuncSetAttribute(k_farn_iter_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FARN_TMA_SMEM));
             attr_done[dev] = c.ok();
@@ -1242,6 +1355,9 @@ void FarnebackEngine::solve(Ctx &c) {
                 else if (quad && knobs.aux_path == 3)  // 80 registers: 3 blocks / SM
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 256, 3>), gf, dim3(256), smem_fast, Ma, Mb,
                                R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
+                else if (quad && knobs.aux_path == 5)  // lane-transposed R1 gather
+                    B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 256, 2, true>), gf, dim3(256),
+                               smem_fast + 8 * 1024, Ma, Mb, R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);
                 else if (quad && knobs.aux_path == 4)  // 64 registers: 4 blocks / SM
                     B2F_LAUNCH(c, CLS_ITER, bytes, (k_farn_iter_fast<6, false, true, 256, 4>), gf, dim3(256), smem_fast, Ma, Mb,
                                R0, R1, lv.fx, lv.fy, h, w, box_inv, win_taps, upd, wflow);

@@ -670,8 +670,8 @@ void Tvl1Engine::device_eps_loop(Ctx &c, int s, const Tvl1Planes &T, const Tvl1B
         Ctx b = c;
         b.stream = bs;
         const double npx = (double)rows * cols;
-        tvl1_tma_launch_dev(b, CLS_ITER, tma_maps(s, 0), B, 0, rows, cols, k, &L_.eps->ia, num_sms_);
-        tvl1_tma_launch_dev(b, CLS_ITER, tma_maps(s, 1), B, 1, rows, cols, k, &L_.eps->ib, num_sms_);
+        tvl1_tma_launch_dev(b, CLS_ITER, tma_maps(s, 0), B, 0, rows, cols, k, &L_.eps->ia, num_sms_, knobs.kernel_path == 0);
+        tvl1_tma_launch_dev(b, CLS_ITER, tma_maps(s, 1), B, 1, rows, cols, k, &L_.eps->ib, num_sms_, knobs.kernel_path == 0);
         B2F_LAUNCH(b, CLS_ITER, 48.0 * npx, k_tvl1_estimate_u, grid, block, 0, T, rows, cols, k, 1, L_.partials,
                    &L_.eps->sample);
         B2F_LAUNCH(b, CLS_REDUCE, 8.0 * nblocks, k_reduce_partials, dim3(1), dim3(256), 0, L_.partials, nblocks,
@@ -746,13 +746,17 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
             const int kk = tvl1_blocked_pick_k(knobs.fused_iters, count - done, rows, cols);
             if (use_tma && knobs.kernel_path == 5)  // packed-FP32 variant: measured 8 % slower than the scalar kernel
                 tvl1_packed_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
+            else if (use_tma && (knobs.kernel_path == 9 || knobs.kernel_path == 11))  // neighbour mbarriers (11: + TMA stores)
+                tvl1_tmanb_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path == 11);
             else if (use_tma && knobs.kernel_path == 8)  // two warp groups half an iteration apart
                 tvl1_tma2g_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
             else if (use_tma && (knobs.kernel_path == 6 || knobs.kernel_path == 7))  // 2x2 / 2x1 thread-block clusters
                 tvl1_cluster_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, 2,
                                     knobs.kernel_path == 6 ? 2 : 1);
-            else if (use_tma)  // 0 / 4: the scalar persistent TMA kernel (3: without elect.sync)
-                tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path != 3);
+            else if (use_tma)  // 0: the scalar persistent TMA kernel, centre tiles leave through TMA stores (+1.9 %,
+                               // DESIGN.md 4.1); 4: the same with the round-1 STG epilogue; 3: 4 without elect.sync
+                tvl1_tma_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path != 3,
+                                knobs.kernel_path != 3 && knobs.kernel_path != 4);
             else
                 tvl1_blocked_launch(c, CLS_ITER, B, cur, rows, cols, k, kk);
             cur ^= 1;

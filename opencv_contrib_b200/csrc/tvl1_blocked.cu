@@ -227,6 +227,135 @@ __device__ __forceinline__ void tile_iterate_2g(Regs &r, float *ex, int iters, c
     __syncthreads();  // both groups are done with the tile (B half an iteration later)
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Neighbour-synchronised variant of tile_iterate (round 2, kernel_path 9).  The source-level profile of the default
+// kernel shows the steady-state loop issuing on 62 % of its cycles: the three CTA-wide barriers of an iteration drain
+// all 16 warps at once (the dual update ends in a sqrt -> rcp -> mul chain), and they keep every warp of an SM
+// sub-partition in the same half iteration -- FP32-issue bound in the primal half, SFU-queue bound in the dual half.
+// But a warp (two thread rows = four pixel rows) only ever needs rows from the warp above (p12/p22, primal update)
+// and the warp below (u1/u2, dual update).  Here every warp owns two mbarriers (arrival count 1):
+//   done_p[w]: "warp w published the bottom rows of p"   -> waited on by warp w+1 before its primal update
+//   done_u[w]: "warp w published the top rows of u"      -> waited on by warp w-1 before its dual update
+// and no CTA-wide barrier is left inside the iterations.  Warps drift apart by up to one half iteration per warp of
+// distance, so the four warps of a sub-partition (w, w+4, w+8, w+12) sit in different halves and fill each other's
+// SFU / FP32 gaps.  mbarrier.try_wait suspends the warp in hardware; a waiting warp issues nothing.
+// Single-buffered exchange stays safe: warp w rewrites its u rows in primal(it) only after done_p[w-1] of dual(it-1),
+// by which time warp w-1 has read them; it rewrites its p rows in dual(it) only after done_u[w+1] of primal(it), by
+// which time warp w+1 has read them.  A producer is never more than one phase ahead of its consumer, so a parity bit
+// per waited barrier is enough.  Same arithmetic per pixel, same operands: bit-identical to tile_iterate.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32_early(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_arrive_release(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32_early(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "NB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra NB_DONE;\n\t"
+        "bra NB_WAIT;\n\t"
+        "NB_DONE:\n\t"
+        "}" ::"r"(smem_u32_early(bar)), "r"(parity) : "memory");
+}
+
+template <bool BORDER>
+__device__ __forceinline__ void tile_iterate_nb(Regs &r, float *ex, uint64_t *nb, uint32_t &par_p, uint32_t &par_u,
+                                                int iters, const Tvl1Scalars k, int lx, int tr, int gxb, int gyb, int W,
+                                                int H) {
+    float *ex_u1 = ex, *ex_u2 = ex + EX_F, *ex_p12 = ex + 2 * EX_F, *ex_p22 = ex + 3 * EX_F;
+    const int mine = tr * R + 4 * lx;
+    const int up = max(tr - 1, 0) * R + 4 * lx;
+    const int dn = min(tr + 1, 31) * R + 4 * lx;
+    const int w = tr >> 1;
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    uint64_t *done_p = nb, *done_u = nb + 16;
+
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
+    if (iters <= 0) return;
+
+    st4(ex_p12 + mine, r.p12[1]);
+    st4(ex_p22 + mine, r.p22[1]);
+    __syncwarp();
+    if (lane0) mbar_arrive_release(done_p + w);
+
+    for (int it = 0; it < iters; ++it) {
+        // ---------------- primal update ----------------
+        if (w > 0) {
+            mbar_wait_parity(done_p + (w - 1), par_p);
+            par_p ^= 1;
+        }
+        float up12[4], up22[4];
+        ld4(ex_p12 + up, up12);
+        ld4(ex_p22 + up, up22);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float l11 = __shfl_up_sync(0xffffffffu, r.p11[j][3], 1, 16);
+            const float l21 = __shfl_up_sync(0xffffffffu, r.p21[j][3], 1, 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float pl11 = i ? r.p11[j][i ? i - 1 : 0] : l11;
+                float pl21 = i ? r.p21[j][i ? i - 1 : 0] : l21;
+                float pu12 = j ? r.p12[0][i] : up12[i];
+                float pu22 = j ? r.p22[0][i] : up22[i];
+                if (BORDER) {
+                    if (gxb + i == 0) { pl11 = 0.f; pl21 = 0.f; }
+                    if (gyb + j == 0) { pu12 = 0.f; pu22 = 0.f; }
+                }
+                float a, b;
+                tvl1_update_u(k, r.Ix[j][i], r.Iy[j][i], r.gr[j][i], r.rc[j][i], r.u1[j][i], r.u2[j][i],
+                              r.p11[j][i], pl11, r.p12[j][i], pu12, r.p21[j][i], pl21, r.p22[j][i], pu22, a, b);
+                r.u1[j][i] = a;
+                r.u2[j][i] = b;
+            }
+        }
+        st4(ex_u1 + mine, r.u1[0]);
+        st4(ex_u2 + mine, r.u2[0]);
+        __syncwarp();
+        if (lane0) mbar_arrive_release(done_u + w);
+
+        // ---------------- dual update ----------------
+        if (w < 15) {
+            mbar_wait_parity(done_u + (w + 1), par_u);
+            par_u ^= 1;
+        }
+        float dn1[4], dn2[4];
+        ld4(ex_u1 + dn, dn1);
+        ld4(ex_u2 + dn, dn2);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float r1 = __shfl_down_sync(0xffffffffu, r.u1[j][0], 1, 16);
+            const float r2 = __shfl_down_sync(0xffffffffu, r.u2[j][0], 1, 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float c1 = r.u1[j][i], c2 = r.u2[j][i];
+                const float ur1 = i < 3 ? r.u1[j][i < 3 ? i + 1 : 3] : r1;
+                const float ur2 = i < 3 ? r.u2[j][i < 3 ? i + 1 : 3] : r2;
+                const float ud1 = j == 0 ? r.u1[1][i] : dn1[i];
+                const float ud2 = j == 0 ? r.u2[1][i] : dn2[i];
+                float ux1 = __fsub_rn(ur1, c1), uy1 = __fsub_rn(ud1, c1);
+                float ux2 = __fsub_rn(ur2, c2), uy2 = __fsub_rn(ud2, c2);
+                if (BORDER) {
+                    if (gxb + i == W - 1) { ux1 = 0.f; ux2 = 0.f; }
+                    if (gyb + j == H - 1) { uy1 = 0.f; uy2 = 0.f; }
+                }
+                tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, r.p11[j][i], r.p12[j][i], r.p21[j][i], r.p22[j][i]);
+            }
+        }
+        if (it + 1 < iters) {  // the rows after the last dual update have no reader: keep arrivals and waits paired
+            st4(ex_p12 + mine, r.p12[1]);
+            st4(ex_p22 + mine, r.p22[1]);
+            __syncwarp();
+            if (lane0) mbar_arrive_release(done_p + w);
+        }
+    }
+}
+
 struct InPlanes {
     Plane p[N_IN];
 };
@@ -346,6 +475,17 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 struct TmaMaps {
     CUtensorMap in[N_IN];
 };
+// Output descriptors of the TMA-store epilogue: the six planes of the state a launch writes, 48 x 48 boxes (the centre
+// tile of an 8-pixel halo).  The tensor extent is the image, so the parts of an edge tile outside it are clipped.
+constexpr int OT = R - 16;            // centre tile edge served by the TMA-store epilogue
+constexpr int OT_F = OT * OT;         // floats per staged output tile
+struct TmaOutMaps {
+    CUtensorMap out[N_OUT];
+};
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(src)) : "memory");
+}
 
 // TMA needs the global address of every box row 16-byte aligned, i.e. the box x-origin a multiple
 // of 4 floats, while region origins are only even (tile*tx - halo).  The box is therefore 8 columns
@@ -381,11 +521,12 @@ __device__ __forceinline__ void store_pairs(float *p, const float (&v)[4], int m
     else if (m1 == 1) p[2] = v[2];
 }
 
-template <bool ELECT, int TBOX_W, bool TWOG = false>
+template <bool ELECT, int TBOX_W, int MODE = 0>  // MODE: 0 CTA barriers, 1 two groups, 2 neighbour mbarriers
 __global__ void __launch_bounds__(NT, 1)
     k_tvl1_blocked_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12,
                        Plane o_p21, Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int tile,
-                       int tiles_x, int ntiles, const int *__restrict__ iters_dev) {
+                       int tiles_x, int ntiles, const int *__restrict__ iters_dev,
+                       const __grid_constant__ TmaOutMaps omaps, int tma_store) {
     constexpr int TPLANE_F = TBOX_W * R;  // floats per staged plane
     if (iters_dev) {  // device-side convergence loop: the iteration count of this pass is decided on the GPU
         iters = __ldg(iters_dev);
@@ -394,7 +535,12 @@ __global__ void __launch_bounds__(NT, 1)
     extern __shared__ __align__(1024) float smem[];
     float *stage = smem;
     float *ex = smem + N_IN * TPLANE_F;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(ex + (TWOG ? 8 : 4) * EX_F);  // two-group variant: exchange double-buffered
+    constexpr bool TWOG = MODE == 1;
+    // two-group variant: exchange double-buffered; TMA-store epilogue: six output tiles alias the exchange arrays
+    constexpr int EX_AREA_F = TWOG ? 8 * EX_F : (TBOX_W == R ? (N_OUT * OT_F > 4 * EX_F ? N_OUT * OT_F : 4 * EX_F) : 4 * EX_F);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ex + EX_AREA_F);
+    uint64_t *nb = bar + 2;  // MODE 2: done_p[16], done_u[16]
+    uint32_t par_p = 0, par_u = 0;
 
     const int tid = threadIdx.x;
     const int lx = tid & 15, tr = tid >> 4;
@@ -402,6 +548,8 @@ __global__ void __launch_bounds__(NT, 1)
 
     if (tid == 0) {
         mbar_init(bar, 1);
+        if (MODE == 2)
+            for (int i = 0; i < 32; ++i) mbar_init(nb + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -447,6 +595,8 @@ __global__ void __launch_bounds__(NT, 1)
             ldrow(8, r.p21[0], r.p21[1]);
             ldrow(9, r.p22[0], r.p22[1]);
         }
+        if (TBOX_W == R && tma_store && issuer)  // the previous tile's TMA stores have read their staging tiles
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();  // the staging buffer is free again
 
         const int tn = t + gridDim.x;
@@ -461,7 +611,12 @@ __global__ void __launch_bounds__(NT, 1)
 
         const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
         const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
-        if (TWOG) {
+        if (MODE == 2) {
+            if (border)
+                tile_iterate_nb<true>(r, ex, nb, par_p, par_u, iters, k, lx, tr, gxb, gyb, cols, rows);
+            else
+                tile_iterate_nb<false>(r, ex, nb, par_p, par_u, iters, k, lx, tr, gxb, gyb, cols, rows);
+        } else if (TWOG) {
             if (border)
                 tile_iterate_2g<true>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
             else
@@ -471,6 +626,36 @@ __global__ void __launch_bounds__(NT, 1)
         else
             tile_iterate<false>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
 
+        if (TBOX_W == R && tma_store) {
+            // centre tile -> six dense 48 x 48 tiles in shared memory (over the exchange arrays) -> one TMA store each.
+            // 12 STS.128 per thread replace 24 predicated STG.64 and their address arithmetic; the copy engine clips
+            // edge tiles against the image.  (halo == 8 and tile == 48 here.)
+            float *ot = ex;
+            if (MODE == 2) __syncthreads();  // no CTA barrier ended the last dual update: neighbours may still read ex
+            const int ox = 4 * lx - 8, oy = 2 * tr - 8;
+            if (ox >= 0 && ox < OT) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (oy + j >= 0 && oy + j < OT) {
+                        float *d = ot + (oy + j) * OT + ox;
+                        st4(d, r.u1[j]);
+                        st4(d + OT_F, r.u2[j]);
+                        st4(d + 2 * OT_F, r.p11[j]);
+                        st4(d + 3 * OT_F, r.p12[j]);
+                        st4(d + 4 * OT_F, r.p21[j]);
+                        st4(d + 5 * OT_F, r.p22[j]);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (issuer) {
+#pragma unroll
+                for (int pl = 0; pl < N_OUT; ++pl) tma_store_2d(&omaps.out[pl], ot + pl * OT_F, tx * tile, ty * tile);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+        }
         // centre tile -> global, 8-byte stores (halo, tile and gx0 are even, so pairs never straddle);
         // all six output planes share one pitch, so one element offset serves them all
         const int rx = 4 * lx;
@@ -492,6 +677,8 @@ __global__ void __launch_bounds__(NT, 1)
             }
         }
     }
+    if (TBOX_W == R && tma_store && issuer)  // the staging tiles must outlive the copy engine's reads of them
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 
@@ -1145,8 +1332,9 @@ bool tma_encode_2d_f32(void *map_out, const float *base, uint64_t width, uint64_
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// one block = two descriptor sets: [0] 72-wide boxes (any even origin), [1] 64-wide boxes (origin % 4 == 0)
-size_t tvl1_tma_maps_bytes() { return 2 * sizeof(TmaMaps); }
+// one block = two input descriptor sets, [0] 72-wide boxes (any even origin), [1] 64-wide boxes (origin % 4 == 0),
+// followed by the output descriptors (48 x 48 boxes on the planes of the other state) of the TMA-store epilogue
+size_t tvl1_tma_maps_bytes() { return 2 * sizeof(TmaMaps) + sizeof(TmaOutMaps); }
 
 bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int rows, int cols) {
     TmaMaps *m = static_cast<TmaMaps *>(dst);
@@ -1156,14 +1344,35 @@ bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int row
         if (!encode_plane(&m[0].in[i], in[i], rows, cols, TBOX_WIDE)) return false;
         if (!encode_plane(&m[1].in[i], in[i], rows, cols, R)) return false;
     }
+    TmaOutMaps *om = reinterpret_cast<TmaOutMaps *>(m + 2);
+    const Tvl1State &so = B.s[cur ^ 1];
+    const Plane out[N_OUT] = {so.u1, so.u2, so.p11, so.p12, so.p21, so.p22};
+    for (int i = 0; i < N_OUT; ++i)
+        if (!tma_encode_2d_f32(&om->out[i], out[i].p, (uint64_t)cols, (uint64_t)rows, (uint64_t)out[i].pitch * sizeof(float),
+                               OT, OT))
+            return false;
     return true;
 }
+static const TmaOutMaps *out_maps(const void *maps) {
+    return reinterpret_cast<const TmaOutMaps *>(static_cast<const TmaMaps *>(maps) + 2);
+}
 
-constexpr size_t smem_tma_bytes(int box_w) { return sizeof(float) * (size_t)(N_IN * box_w * R + 4 * EX_F) + 64; }
+// exchange area: four exchange arrays; the 64-wide-box kernels keep room for the six 48 x 48 output tiles of the
+// TMA-store epilogue there (they alias the exchange arrays), the two-group kernel for its second set of arrays
+constexpr size_t ex_area_floats(int box_w, int mode) {
+    return mode == 1 ? 8 * (size_t)EX_F
+                     : (box_w == R && (size_t)N_OUT * OT_F > 4 * (size_t)EX_F ? (size_t)N_OUT * OT_F : 4 * (size_t)EX_F);
+}
+constexpr size_t smem_tma_bytes(int box_w, int mode = 0) {
+    return sizeof(float) * ((size_t)N_IN * box_w * R + ex_area_floats(box_w, mode)) + 64 + (mode == 2 ? 256 : 0);
+}
+static_assert(smem_tma_bytes(R, 0) <= 227 * 1024 && smem_tma_bytes(R, 1) <= 227 * 1024 && smem_tma_bytes(R, 2) <= 227 * 1024,
+              "TV-L1 TMA kernel: shared memory over the 227 KB limit");
 
 void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
-                     const Tvl1Scalars &k, int iters, int num_sms, bool elect) {
+                     const Tvl1Scalars &k, int iters, int num_sms, bool elect, bool tma_store) {
     const Tvl1State &so = B.s[cur ^ 1];
+    const TmaOutMaps *om = out_maps(maps);
     const int halo = (iters + 1) & ~1;  // even halo >= iters keeps every store 8-byte aligned
     const int tile = R - 2 * halo;
     const int tiles_x = div_up(cols, tile), tiles_y = div_up(rows, tile);
@@ -1174,15 +1383,16 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
     const TmaMaps *m = static_cast<const TmaMaps *>(maps) + (aligned ? 1 : 0);
     if (aligned)
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R>), dim3(grid), dim3(NT), smem_tma_bytes(R), *m, so.u1,
-                   so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr);
+                   so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr, *om,
+                   (tma_store && halo == 8) ? 1 : 0);
     else if (elect)
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, TBOX_WIDE>), dim3(grid), dim3(NT),
                    smem_tma_bytes(TBOX_WIDE), *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
-                   halo, tile, tiles_x, ntiles, nullptr);
+                   halo, tile, tiles_x, ntiles, nullptr, *om, 0);
     else
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<false, TBOX_WIDE>), dim3(grid), dim3(NT),
                    smem_tma_bytes(TBOX_WIDE), *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
-                   halo, tile, tiles_x, ntiles, nullptr);
+                   halo, tile, tiles_x, ntiles, nullptr, *om, 0);
 }
 
 // Two-group (anti-phase) variant of the aligned kernel; halo rounded up to a multiple of 4 like the packed kernel.
@@ -1196,14 +1406,31 @@ void tvl1_tma2g_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlane
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     const double bytes = 64.0 * (double)rows * cols * iters;
     const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;
-    B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R, true>), dim3(grid), dim3(NT), smem_tma_bytes(R) + sizeof(float) * 4 * EX_F,
-               *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr);
+    B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R, 1>), dim3(grid), dim3(NT), smem_tma_bytes(R, 1),
+               *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr,
+               *out_maps(maps), 0);
+}
+
+// Neighbour-synchronised variant of the aligned kernel (kernel_path 9).
+void tvl1_tmanb_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                       const Tvl1Scalars &k, int iters, int num_sms, bool tma_store) {
+    const Tvl1State &so = B.s[cur ^ 1];
+    const int halo = (iters + 3) & ~3;
+    const int tile = R - 2 * halo;
+    const int tiles_x = div_up(cols, tile), tiles_y = div_up(rows, tile);
+    const int ntiles = tiles_x * tiles_y;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    const double bytes = 64.0 * (double)rows * cols * iters;
+    const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;
+    B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R, 2>), dim3(grid), dim3(NT), smem_tma_bytes(R, 2), *m, so.u1,
+               so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr,
+               *out_maps(maps), (tma_store && halo == 8) ? 1 : 0);
 }
 
 // One pass whose iteration count (0..8; negative = skip the pass) is read from device memory at run time: fixed
 // geometry (8-pixel halo, 48-pixel tiles, 64-wide boxes) so the launch can sit in a CUDA graph's while-loop body.
 void tvl1_tma_launch_dev(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
-                         const Tvl1Scalars &k, const int *iters_dev, int num_sms) {
+                         const Tvl1Scalars &k, const int *iters_dev, int num_sms, bool tma_store) {
     const Tvl1State &so = B.s[cur ^ 1];
     const int halo = 8, tile = R - 2 * halo;
     const int tiles_x = div_up(cols, tile), tiles_y = div_up(rows, tile);
@@ -1211,7 +1438,8 @@ void tvl1_tma_launch_dev(Ctx &c, int cls, const void *maps, const Tvl1BlockedPla
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;
     B2F_LAUNCH(c, cls, 0.0, (k_tvl1_blocked_tma<true, R>), dim3(grid), dim3(NT), smem_tma_bytes(R), *m, so.u1, so.u2,
-               so.p11, so.p12, so.p21, so.p22, rows, cols, k, 0, halo, tile, tiles_x, ntiles, iters_dev);
+               so.p11, so.p12, so.p21, so.p22, rows, cols, k, 0, halo, tile, tiles_x, ntiles, iters_dev, *out_maps(maps),
+               tma_store ? 1 : 0);
 }
 
 constexpr size_t smem_packed_bytes() { return sizeof(float) * (size_t)(N_IN * R * R) + sizeof(float4) * 4 * PEX_F4 + 64; }
@@ -1308,8 +1536,11 @@ cudaError_t tvl1_blocked_init() {
         e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_tma_bytes(R));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(smem_tma_bytes(R) + sizeof(float) * 4 * EX_F));
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_tma_bytes(R, 1));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_tma_bytes(R, 2));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_tvl1_packed_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_packed_bytes());

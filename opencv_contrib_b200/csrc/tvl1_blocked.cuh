@@ -49,13 +49,15 @@ void tvl1_blocked_launch(Ctx &c, int cls, const Tvl1BlockedPlanes &B, int cur, i
 size_t tvl1_tma_maps_bytes();
 bool tvl1_tma_build_maps(void *dst, const Tvl1BlockedPlanes &B, int cur, int rows, int cols);
 void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
-                     const Tvl1Scalars &k, int iters, int num_sms, bool elect = true);
+                     const Tvl1Scalars &k, int iters, int num_sms, bool elect = true, bool tma_store = false);
 
 // Same kernel, iteration count read from device memory when the pass runs (device-side convergence loop).
 void tvl1_tma_launch_dev(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
-                         const Tvl1Scalars &k, const int *iters_dev, int num_sms);
+                         const Tvl1Scalars &k, const int *iters_dev, int num_sms, bool tma_store);
 
 // Two-group variant: the two halves of the region run half an iteration apart (FP32-bound primal against SFU-bound dual).
+void tvl1_tmanb_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                       const Tvl1Scalars &k, int iters, int num_sms, bool tma_store);
 void tvl1_tma2g_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                        const Tvl1Scalars &k, int iters, int num_sms);
 

@@ -62,7 +62,7 @@ def test_blocked_kernel_bit_identical_to_unfused(cuda_device, K):
     # DSMEM ghost exchange, 2 = blocked kernel with plain loads
     import os
     # 8 = two warp groups half an iteration apart (named barriers)
-    paths = (0, 5, 2) if os.environ.get("B2F_SKIP_CLUSTER") else (0, 5, 6, 7, 8, 2)
+    paths = (0, 4, 5, 9, 11, 2) if os.environ.get("B2F_SKIP_CLUSTER") else (0, 4, 5, 6, 7, 8, 9, 11, 2)
     for path in paths:
         for graph in (0, 1):
             b, _ = _run(cuda_device, I0, I1, path=path, fused=K, graph=graph, **kw)

@@ -6,12 +6,13 @@ import numpy as np, torch
 import opencv_contrib_b200 as ocb
 from oracle import synth
 dev = torch.device("cuda:0")
+PATHS = tuple(int(a) for a in sys.argv[1:]) or (0, 6, 7, 8, 9)  # path 0 first: it is the comparison base
 ok = True
 for (h, w) in [(203, 277), (540, 960)]:
     I0, I1, _ = synth.make_pair(h, w, seed=3, kind="smooth")
     d0, d1 = torch.from_numpy(I0).to(dev), torch.from_numpy(I1).to(dev)
     outs = {}
-    for path in (0, 6, 7, 8):
+    for path in PATHS:
         for K in (8, 3):
             alg = ocb.OpticalFlowDual_TVL1_create(nscales=3, warps=2, epsilon=0.0, iterations=23)
             alg.setEngineOption("kernel_path", path)
