@@ -166,10 +166,12 @@ typedef enum b2f_param_id {
                                      elect.sync, 4 = TMA loads with the round-1 STG epilogue, 5 = packed-FP32 (f32x2)
                                      TMA kernel, 6 / 7 = 2x2 / 2x1-cluster kernels, 8 = two warp groups half an
                                      iteration apart, 9 = warps synchronise with their neighbours through mbarriers
-                                     (11 = 9 with the TMA-store epilogue).  All bit-identical; 0 is the fastest.   */
-    B2F_ENGINE_AUX_PATH = 903     /* variant of the secondary kernels.  TV-L1: 0 = separable warp kernel (40
-                                     registers), 1 = tap-by-tap warp kernel (accumulation in the reference's
-                                     order), 2 = separable at 32 registers.  Farneback: fused iteration kernel
+                                     (11 = 9 with the TMA-store epilogue), 12 = row-skewed iterations behind
+                                     split-phase mbarriers.  All bit-identical; 0 is the fastest.                  */
+    B2F_ENGINE_AUX_PATH = 903     /* variant of the secondary kernels.  TV-L1 warp: 0 = tiled kernel (I1 window of a
+                                     64x32 tile staged in shared memory by TMA), 1 = tap-by-tap kernel (accumulation
+                                     in the reference's order), 2 / 3 = separable kernel at 32 / 40 registers; 0, 2
+                                     and 3 are bit-identical.  Farneback: fused iteration kernel
                                      at 0 = 128 registers (2 blocks / SM), 3 = 80, 4 = 64 registers, 5 = R1 gather
                                      with lanes on consecutive pixels (measured slower)                      */
 } b2f_param_id;

@@ -15,6 +15,8 @@
 #include "tvl1_math.cuh"
 #include "tvl1_blocked.cuh"
 
+#include <cuda.h>  // CUtensorMap (type only; encoded through tma_encode_2d_f32)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -38,6 +40,9 @@ struct Tvl1Planes {
 // The gradients of I1 are formed on the fly from a 6x6 window of I1 (same 0.5f*(a-b) arithmetic
 // as the reference's separate gradient pass, so I1x/I1y never touch HBM); taps use clamp
 // addressing exactly like the reference's point/clamp textures; I1w is not stored (dead).
+// The `grad` plane receives the thresholding constant tvl1_inv_grad(|grad I1w|^2) = 1/|grad|^2 (or the huge stand-in
+// for a zero gradient) instead of |grad|^2 itself: every consumer wants the reciprocal, it is constant over a warp's
+// inner iterations, and the iteration kernels used to recompute it for every tile of every pass.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx, Plane I1wy,
                                                    Plane grad, Plane rho, int rows, int cols) {
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(256) k_tvl1_warp(Plane I0, Plane I1, Plane u1p
     const float Iy = sumy * coeff;
     I1wx.at(y, x) = Ix;
     I1wy.at(y, x) = Iy;
-    grad.at(y, x) = __fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix));
+    grad.at(y, x) = tvl1_inv_grad(__fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix)));  // the thresholding constant, not |grad|^2
     rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
 }
 
@@ -153,7 +158,7 @@ __device__ __forceinline__ void keys_weights(float t, float (&k)[4]) {
     k[3] = (0.5f * t - 0.5f) * t * t;
 }
 
-// Separable form of the same warp (round 2, the default): w_ij = kx[i] * ky[j], so the three weighted sums are row
+// Separable form of the same warp (round 2; aux_path 3, and the fallback for levels smaller than one staged box): w_ij = kx[i] * ky[j], so the three weighted sums are row
 // sums r[j] = sum_i kx[i] W[j][i+1] (6 rows), rx[j] = sum_i kx[i] (W[j][i+2] - W[j][i]) (4 rows) combined with ky:
 //   I1w = sum_j ky[j] r[j+1],  I1wx = 0.5 sum_j ky[j] rx[j+1],  I1wy = 0.5 sum_j ky[j] (r[j+2] - r[j]),
 // about half the arithmetic of the tap-by-tap form (kept as aux_path 1; the few pixels whose window touches the image
@@ -212,8 +217,170 @@ __global__ void __launch_bounds__(256, MINB) k_tvl1_warp_sep(Plane I0, Plane I1,
     const float Iy = sumy * coeff;
     I1wx.at(y, x) = Ix;
     I1wy.at(y, x) = Iy;
-    grad.at(y, x) = __fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix));
+    grad.at(y, x) = tvl1_inv_grad(__fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix)));  // the thresholding constant, not |grad|^2
     rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiled warp kernel (round 2, the default, aux_path 0): the separable warp above executes 325 instructions per pixel, most of
+// them 64-bit address arithmetic for its 32 global loads plus the spills of its 40-register cap, and waits on two
+// dependent global round trips (ncu: long_scoreboard 7.1 per issue).  Here one CTA owns a 64 x 32 pixel tile and the
+// copy engine stages the (64 + 24) x (32 + 24) window of I1 around it in shared memory (one cp.async.bulk.tensor per
+// CTA, issued before the flow is even read).  A pixel whose 6 x 6 tap window lies inside the staged box -- any flow
+// up to 9 pixels -- gathers its taps with LDS at compile-time offsets from ONE 32-bit base address; the others take
+// the global-memory window (same arithmetic, out of line) or, at the image border, the clamped tap loop.  Same
+// expressions in the same order as k_tvl1_warp_sep: bit-identical to it (tested).
+// ---------------------------------------------------------------------------------------------
+constexpr int WT_W = 64, WT_H = 32, WT_M = 12;
+constexpr int WB_W = WT_W + 2 * WT_M, WB_H = WT_H + 2 * WT_M;  // 88 x 56 floats = 19 712 bytes
+constexpr int WT_THREADS = 256;
+
+__device__ __forceinline__ uint32_t wt_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wt_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WT_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WT_DONE;\n\t"
+        "bra WT_WAIT;\n\t"
+        "WT_DONE:\n\t"
+        "}" ::"r"(wt_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// The six-row separable accumulation of k_tvl1_warp_sep on a window whose top-left tap is base[0]; STRIDE > 0: shared
+// memory rows of STRIDE floats (every offset an immediate), STRIDE == 0: global rows of `pitch` floats.
+template <int STRIDE>
+__device__ __forceinline__ void warp_sep_window(const float *base, size_t pitch, const float (&kx)[4], const float (&ky)[4],
+                                                float &sum, float &sumx, float &sumy) {
+    float r[6], rx[4];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const float *row = STRIDE ? base + j * STRIDE : base + (size_t)j * pitch;
+        const float a1 = STRIDE ? row[1] : __ldg(row + 1), a2 = STRIDE ? row[2] : __ldg(row + 2);
+        const float a3 = STRIDE ? row[3] : __ldg(row + 3), a4 = STRIDE ? row[4] : __ldg(row + 4);
+        r[j] = __fmaf_rn(kx[3], a4, __fmaf_rn(kx[2], a3, __fmaf_rn(kx[1], a2, kx[0] * a1)));
+        if (j >= 1 && j <= 4) {
+            const float a0 = STRIDE ? row[0] : __ldg(row), a5 = STRIDE ? row[5] : __ldg(row + 5);
+            rx[j - 1] = __fmaf_rn(kx[3], a5 - a3, __fmaf_rn(kx[2], a4 - a2, __fmaf_rn(kx[1], a3 - a1, kx[0] * (a2 - a0))));
+        }
+    }
+    sum = __fmaf_rn(ky[3], r[4], __fmaf_rn(ky[2], r[3], __fmaf_rn(ky[1], r[2], ky[0] * r[1])));
+    sumx = 0.5f * __fmaf_rn(ky[3], rx[3], __fmaf_rn(ky[2], rx[2], __fmaf_rn(ky[1], rx[1], ky[0] * rx[0])));
+    sumy = 0.5f * __fmaf_rn(ky[3], r[5] - r[3], __fmaf_rn(ky[2], r[4] - r[2], __fmaf_rn(ky[1], r[3] - r[1], ky[0] * (r[2] - r[0]))));
+}
+
+// Pixels whose window left the staged box (flow beyond the margin) or touches the image border.  A real call on purpose;
+// weights and results travel in registers (arrays passed by reference would pin them to the stack in the hot path too).
+__device__ __noinline__ float3 warp_slow_taps(const Plane I1, int rows, int cols, int ix, int iy, float kx0, float kx1,
+                                              float kx2, float kx3, float ky0, float ky1, float ky2, float ky3) {
+    const float kx[4] = {kx0, kx1, kx2, kx3}, ky[4] = {ky0, ky1, ky2, ky3};
+    float sum, sumx, sumy;
+    if (ix >= 1 && iy >= 1 && ix + 4 <= cols - 1 && iy + 4 <= rows - 1)
+        warp_sep_window<0>(&I1.at(iy - 1, ix - 1), (size_t)I1.pitch, kx, ky, sum, sumx, sumy);
+    else
+        warp_border_taps(I1, rows, cols, ix, iy, kx, ky, sum, sumx, sumy);
+    return make_float3(sum, sumx, sumy);
+}
+
+// Per-pixel set-up and write-back shared by the two phases of the tiled kernel (same expressions as k_tvl1_warp_sep).
+__device__ __forceinline__ void warp_px_setup(int x, int y, float u1, float u2, int rows, int cols, int &ix, int &iy,
+                                              float (&kx)[4], float (&ky)[4], float &wsum) {
+    const float wx = x + u1;
+    const float wy = y + u2;
+    const float fx = floorf(wx), fy = floorf(wy);
+    ix = static_cast<int>(fminf(fmaxf(fx, -8.f), cols + 8.f)) - 1;
+    iy = static_cast<int>(fminf(fmaxf(fy, -8.f), rows + 8.f)) - 1;
+    keys_weights(wx - fx, kx);
+    keys_weights(wy - fy, ky);
+    wsum = ((kx[0] + kx[1]) + (kx[2] + kx[3])) * ((ky[0] + ky[1]) + (ky[2] + ky[3]));
+}
+__device__ __forceinline__ void warp_px_finish(int x, int y, float u1, float u2, float I0v, float sum, float sumx, float sumy,
+                                               float wsum, Plane I1wx, Plane I1wy, Plane grad, Plane rho) {
+    const float coeff = 1.0f / wsum;
+    const float I1w = sum * coeff;
+    const float Ix = sumx * coeff;
+    const float Iy = sumy * coeff;
+    I1wx.at(y, x) = Ix;
+    I1wy.at(y, x) = Iy;
+    grad.at(y, x) = tvl1_inv_grad(__fmaf_rn(Iy, Iy, __fmul_rn(Ix, Ix)));  // the thresholding constant, not |grad|^2
+    rho.at(y, x) = __fsub_rn(__fmaf_rn(-Iy, u2, __fmaf_rn(-Ix, u1, I1w)), I0v);
+}
+
+// Phase 1: every thread walks its 8 pixels; a pixel whose window lies in the staged box is finished on the spot, the
+// others (image border, flow beyond the margin) are only queued.  Phase 2: the CTA's queue is worked off one pixel per
+// thread.  (Handling them in place was measured first: a warp on the left / right image edge then makes 8 slow calls in
+// a row and every launch ends ~25 us late, whatever the image size.)
+__global__ void __launch_bounds__(WT_THREADS, 3)
+    k_tvl1_warp_tile(const __grid_constant__ CUtensorMap mapI1, Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx,
+                     Plane I1wy, Plane grad, Plane rho, int rows, int cols) {
+    __shared__ __align__(128) float win[WB_H * WB_W];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int q_count;
+    __shared__ unsigned short q_px[WT_W * WT_H];  // queued pixels, (row in tile) * 64 + (column in tile)
+    const int tid = threadIdx.x;
+    const int bx0 = blockIdx.x * WT_W - WT_M, by0 = blockIdx.y * WT_H - WT_M;  // box origin (x a multiple of 4: TMA rule)
+    if (tid == 0) {
+        q_count = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wt_smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wt_smem_u32(&bar)),
+                     "r"((uint32_t)(WB_W * WB_H * sizeof(float))) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(wt_smem_u32(win)), "l"(reinterpret_cast<uint64_t>(&mapI1)), "r"(bx0), "r"(by0), "r"(wt_smem_u32(&bar))
+            : "memory");
+    }
+    // warp w: columns 32 (w & 1) .. +31 of the tile, rows (w >> 1) + 4 k, k = 0..7 -- a warp's lanes are 32 consecutive
+    // pixels of one row, so its taps are (for a smooth flow) consecutive shared-memory words
+    const int lx = tid & 63, ly0 = tid >> 6;
+    const int x = blockIdx.x * WT_W + lx;
+    const int yb = blockIdx.y * WT_H + ly0;
+    const bool xin = x < cols;
+    float nu1 = 0.f, nu2 = 0.f, nI0 = 0.f;
+    if (xin && yb < rows) {
+        nu1 = __ldg(&u1p.at(yb, x));
+        nu2 = __ldg(&u2p.at(yb, x));
+        nI0 = __ldg(&I0.at(yb, x));
+    }
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    wt_mbar_wait(&bar, 0);
+#pragma unroll 1
+    for (int k = 0; k < WT_H / 4; ++k) {
+        const int y = yb + 4 * k;
+        const float u1 = nu1, u2 = nu2, I0v = nI0;
+        if (k + 1 < WT_H / 4 && xin && y + 4 < rows) {  // next pixel's streaming operands travel under this one's taps
+            nu1 = __ldg(&u1p.at(y + 4, x));
+            nu2 = __ldg(&u2p.at(y + 4, x));
+            nI0 = __ldg(&I0.at(y + 4, x));
+        }
+        if (!xin || y >= rows) continue;
+        int ix, iy;
+        float kx[4], ky[4], wsum;
+        warp_px_setup(x, y, u1, u2, rows, cols, ix, iy, kx, ky, wsum);
+        const int sx = ix - 1 - bx0, sy = iy - 1 - by0;  // the window's top-left tap in box coordinates
+        const bool inside = ix >= 1 && iy >= 1 && ix + 4 <= cols - 1 && iy + 4 <= rows - 1;
+        if (inside && sx >= 0 && sy >= 0 && sx + 5 < WB_W && sy + 5 < WB_H) {
+            float sum, sumx, sumy;
+            warp_sep_window<WB_W>(win + sy * WB_W + sx, 0, kx, ky, sum, sumx, sumy);
+            warp_px_finish(x, y, u1, u2, I0v, sum, sumx, sumy, wsum, I1wx, I1wy, grad, rho);
+        } else {
+            q_px[atomicAdd(&q_count, 1)] = (unsigned short)((ly0 + 4 * k) * WT_W + lx);
+        }
+    }
+    __syncthreads();
+    const int nq = q_count;
+    for (int q = tid; q < nq; q += WT_THREADS) {
+        const int e = q_px[q];
+        const int qx = blockIdx.x * WT_W + (e & (WT_W - 1)), qy = blockIdx.y * WT_H + (e >> 6);
+        const float u1 = __ldg(&u1p.at(qy, qx)), u2 = __ldg(&u2p.at(qy, qx)), I0v = __ldg(&I0.at(qy, qx));
+        int ix, iy;
+        float kx[4], ky[4], wsum;
+        warp_px_setup(qx, qy, u1, u2, rows, cols, ix, iy, kx, ky, wsum);
+        const float3 t = warp_slow_taps(I1, rows, cols, ix, iy, kx[0], kx[1], kx[2], kx[3], ky[0], ky[1], ky[2], ky[3]);
+        warp_px_finish(qx, qy, u1, u2, I0v, t.x, t.y, t.z, wsum, I1wx, I1wy, grad, rho);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -239,11 +406,11 @@ __global__ void __launch_bounds__(256) k_tvl1_estimate_u(Tvl1Planes P, int rows,
         const float p22u = y > 0 ? P.p22.at(y - 1, x) : 0.f;
         float u1n, u2n;
         if (k.gamma == 0.f) {
-            tvl1_update_u(k, Ix, Iy, tvl1_inv_grad(g), rc, u1, u2, p11, p11l, p12, p12u, p21, p21l, p22, p22u, u1n, u2n);
+            tvl1_update_u(k, Ix, Iy, g, rc, u1, u2, p11, p11l, p12, p12u, p21, p21l, p22, p22u, u1n, u2n);
         } else {
             const float u3 = P.u3.at(y, x);
             const float rho = __fadd_rn(rc, __fmaf_rn(k.gamma, u3, __fmaf_rn(Iy, u2, __fmul_rn(Ix, u1))));
-            const float fi = tvl1_threshold(rho, tvl1_inv_grad(g), k.l_t);
+            const float fi = tvl1_threshold(rho, g, k.l_t);
             const float v1 = __fmaf_rn(fi, Ix, u1);
             const float v2 = __fmaf_rn(fi, Iy, u2);
             const float v3 = __fmaf_rn(fi, k.gamma, u3);
@@ -441,6 +608,7 @@ public:
         if (err_host) cudaFreeHost(err_host);
         if (iters_host_) cudaFreeHost(iters_host_);
         free(tma_maps_);
+        free(warp_maps_);
         destroy_graph();
     }
 
@@ -484,6 +652,7 @@ private:
     // TMA descriptor blocks, [level][direction], built once per workspace (host memory, 64 B aligned)
     void *tma_maps_ = nullptr;
     bool tma_ok_ = false;
+    CUtensorMap *warp_maps_ = nullptr;  // one I1 descriptor per level for the tiled warp kernel; null = not available
     int num_sms_ = 0;
     const void *tma_maps(int level, int cur) const {
         return static_cast<const char *>(tma_maps_) + (size_t)(level * 2 + cur) * tvl1_tma_maps_bytes();
@@ -610,6 +779,19 @@ cudaError_t Tvl1Engine::ensure_workspace(int rows, int cols) {
     free(tma_maps_);
     tma_maps_ = nullptr;
     tma_ok_ = false;
+    free(warp_maps_);
+    warp_maps_ = nullptr;
+    if (!getenv("B2F_DISABLE_TMA")) {
+        warp_maps_ = static_cast<CUtensorMap *>(aligned_alloc(64, sizeof(CUtensorMap) * (size_t)L_.nscales));
+        for (int s = 0; warp_maps_ && s < L_.nscales; ++s) {
+            const Level &lv = L_.levels[s];
+            if (!tma_encode_2d_f32(&warp_maps_[s], lv.I1.p, (uint64_t)lv.cols, (uint64_t)lv.rows,
+                                   (uint64_t)lv.I1.pitch * sizeof(float), WB_W, WB_H)) {
+                free(warp_maps_);
+                warp_maps_ = nullptr;
+            }
+        }
+    }
     if (!L_.gamma && !getenv("B2F_DISABLE_TMA")) {
         const size_t mb = tvl1_tma_maps_bytes();
         const size_t total = (mb * 2 * L_.nscales + 63) & ~size_t(63);
@@ -748,6 +930,8 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
                 tvl1_packed_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
             else if (use_tma && (knobs.kernel_path == 9 || knobs.kernel_path == 11))  // neighbour mbarriers (11: + TMA stores)
                 tvl1_tmanb_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, knobs.kernel_path == 11);
+            else if (use_tma && knobs.kernel_path == 12)  // row-skewed iterations behind split-phase barriers
+                tvl1_tmasp_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_, true);
             else if (use_tma && knobs.kernel_path == 8)  // two warp groups half an iteration apart
                 tvl1_tma2g_launch(c, CLS_ITER, tma_maps(s, cur), B, cur, rows, cols, k, kk, num_sms_);
             else if (use_tma && (knobs.kernel_path == 6 || knobs.kernel_path == 7))  // 2x2 / 2x1 thread-block clusters
@@ -782,13 +966,20 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
 
     for (int w = 0; w < P.warps; ++w) {
         point_T_at(cur);
-        if (knobs.aux_path == 1)  // tap-by-tap accumulation in the reference's order (62 registers, 4 blocks / SM)
+        // aux_path: 0 tiled (the default; levels smaller than one staged box take the separable kernel), 1 tap-by-tap in the
+        // reference's order (62 registers, 4 blocks / SM), 2 separable at 32 registers (8 blocks / SM), 3 separable at 40
+        // registers (6 blocks / SM; the default before the tiled kernel)
+        if (knobs.aux_path == 0 && warp_maps_ && cols >= WB_W && rows >= WB_H)  // I1 window staged by the copy engine
+            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_tile, dim3(div_up(cols, WT_W), div_up(rows, WT_H)),
+                       dim3(WT_THREADS), 0, warp_maps_[s], lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy, T.grad, T.rho_c, rows,
+                       cols);
+        else if (knobs.aux_path == 1)
             B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy,
                        T.grad, T.rho_c, rows, cols);
-        else if (knobs.aux_path == 2)  // separable form at 32 registers (8 blocks / SM)
+        else if (knobs.aux_path == 2)
             B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_sep<8>, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx,
                        T.I1wy, T.grad, T.rho_c, rows, cols);
-        else  // separable form at 40 registers (6 blocks / SM): the default
+        else
             B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_sep<6>, grid, block, 0, lv.I0, lv.I1, T.u1, T.u2, T.I1wx,
                        T.I1wy, T.grad, T.rho_c, rows, cols);
 

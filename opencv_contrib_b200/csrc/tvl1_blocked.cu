@@ -2,6 +2,9 @@
 #include "tvl1_blocked.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace b2f {
 
@@ -38,11 +41,6 @@ __device__ __forceinline__ void tile_iterate(Regs &r, float *ex, int iters, cons
     const int up = max(tr - 1, 0) * R + 4 * lx;
     const int dn = min(tr + 1, 31) * R + 4 * lx;
 
-    // |grad I|^2 is constant over the iterations: turn it into the thresholding constant once
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
 
     // publish the bottom rows of p12/p22 for the first primal update
     st4(ex_p12 + mine, r.p12[1]);
@@ -139,10 +137,6 @@ __device__ __forceinline__ void tile_iterate_2g(Regs &r, float *ex, int iters, c
     const int warp = tr >> 1;            // 0..15
     const int gbar = 1 + grp;
 
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
 
     st4(ex + 2 * EX_F + mine, r.p12[1]);   // parity 0
     st4(ex + 3 * EX_F + mine, r.p22[1]);
@@ -273,10 +267,6 @@ __device__ __forceinline__ void tile_iterate_nb(Regs &r, float *ex, uint64_t *nb
     const bool lane0 = (threadIdx.x & 31) == 0;
     uint64_t *done_p = nb, *done_u = nb + 16;
 
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
     if (iters <= 0) return;
 
     st4(ex_p12 + mine, r.p12[1]);
@@ -352,6 +342,132 @@ __device__ __forceinline__ void tile_iterate_nb(Regs &r, float *ex, uint64_t *nb
             st4(ex_p22 + mine, r.p22[1]);
             __syncwarp();
             if (lane0) mbar_arrive_release(done_p + w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-skewed variant of tile_iterate (round 2, kernel_path 12).  Phase clocks of the default kernel (tools/
+// gpu_probe_tile_clocks.py): 1793 cycles per iteration against 1332 issue slots per scheduler -- every warp runs into the
+// CTA barrier right after publishing its row, and the dual half iteration is bound by the SFU on its own (24 MUFU per
+// thread against 177 instructions).  But only ONE of a thread's two pixel rows depends on another thread in each half:
+//   P(top)    needs p(bottom row of the thread above)          P(bottom) needs this thread's own rows only
+//   D(bottom) needs u(top row of the thread below)             D(top)    needs this thread's own rows only
+// so the independent row is moved BEHIND the publication, between a split-phase arrive and its wait:
+//   wait B | P_n(top), publish u(top), arrive A | D_n(top) | wait A | D_n(bottom), publish p(bottom), arrive B | P_n+1(bottom)
+// Two mbarriers (one arrival per warp) replace the two __syncthreads; by the time a warp polls a barrier the other
+// warps had a four-pixel update's time to arrive, and SFU-heavy and FP32-only segments alternate twice per iteration.
+// Single-buffered exchange stays safe: u(top) is rewritten after wait B of the next iteration, i.e. after every warp
+// arrived on B, which each does after its read of the neighbour's u; p(bottom) is rewritten after wait A, which every
+// warp reaches after its read of the neighbour's p.  Same arithmetic per pixel, same operands: bit-identical.
+// ---------------------------------------------------------------------------------------------
+// split-phase barrier helpers on 32-bit shared addresses formed once per tile; the arrival is predicated, not branched
+__device__ __forceinline__ void sp_arrive(uint32_t bar_addr, uint32_t leader) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "@p mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n\t"
+        "}" ::"r"(bar_addr), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void sp_wait(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SP_WAIT:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SP_DONE;\n\t"
+        "bra SP_WAIT;\n\t"
+        "SP_DONE:\n\t"
+        "}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+
+template <bool BORDER, int J>
+__device__ __forceinline__ void sp_primal_row(Regs &r, const Tvl1Scalars &k, const float (&pu12)[4], const float (&pu22)[4],
+                                              int gxb, int gyb) {
+    const float l11 = __shfl_up_sync(0xffffffffu, r.p11[J][3], 1, 16);
+    const float l21 = __shfl_up_sync(0xffffffffu, r.p21[J][3], 1, 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float pl11 = i ? r.p11[J][i ? i - 1 : 0] : l11;
+        float pl21 = i ? r.p21[J][i ? i - 1 : 0] : l21;
+        float u12 = pu12[i], u22 = pu22[i];
+        if (BORDER) {
+            if (gxb + i == 0) { pl11 = 0.f; pl21 = 0.f; }
+            if (gyb + J == 0) { u12 = 0.f; u22 = 0.f; }
+        }
+        float a, b;
+        tvl1_update_u(k, r.Ix[J][i], r.Iy[J][i], r.gr[J][i], r.rc[J][i], r.u1[J][i], r.u2[J][i], r.p11[J][i], pl11,
+                      r.p12[J][i], u12, r.p21[J][i], pl21, r.p22[J][i], u22, a, b);
+        r.u1[J][i] = a;
+        r.u2[J][i] = b;
+    }
+}
+template <bool BORDER, int J>
+__device__ __forceinline__ void sp_dual_row(Regs &r, const Tvl1Scalars &k, const float (&dn1)[4], const float (&dn2)[4],
+                                            int gxb, int gyb, int W, int H) {
+    const float r1 = __shfl_down_sync(0xffffffffu, r.u1[J][0], 1, 16);
+    const float r2 = __shfl_down_sync(0xffffffffu, r.u2[J][0], 1, 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float c1 = r.u1[J][i], c2 = r.u2[J][i];
+        const float ur1 = i < 3 ? r.u1[J][i < 3 ? i + 1 : 3] : r1;
+        const float ur2 = i < 3 ? r.u2[J][i < 3 ? i + 1 : 3] : r2;
+        float ux1 = __fsub_rn(ur1, c1), uy1 = __fsub_rn(dn1[i], c1);
+        float ux2 = __fsub_rn(ur2, c2), uy2 = __fsub_rn(dn2[i], c2);
+        if (BORDER) {
+            if (gxb + i == W - 1) { ux1 = 0.f; ux2 = 0.f; }
+            if (gyb + J == H - 1) { uy1 = 0.f; uy2 = 0.f; }
+        }
+        tvl1_update_p2(k.taut, ux1, uy1, ux2, uy2, r.p11[J][i], r.p12[J][i], r.p21[J][i], r.p22[J][i]);
+    }
+}
+
+template <bool BORDER>
+__device__ __forceinline__ void tile_iterate_sp(Regs &r, float *ex, uint64_t *ab, uint32_t &par_a, uint32_t &par_b, int iters,
+                                                const Tvl1Scalars k, int lx, int tr, int gxb, int gyb, int W, int H) {
+    float *ex_u1 = ex, *ex_u2 = ex + EX_F, *ex_p12 = ex + 2 * EX_F, *ex_p22 = ex + 3 * EX_F;
+    const int mine = tr * R + 4 * lx;
+    const int up = max(tr - 1, 0) * R + 4 * lx;
+    const int dn = min(tr + 1, 31) * R + 4 * lx;
+    const uint32_t lane0 = (threadIdx.x & 31) == 0 ? 1u : 0u;
+    // A: "u(top) published", B: "p(bottom) published"; 16 arrivals (one per warp) each
+    const uint32_t bar_a = smem_u32_early(ab), bar_b = bar_a + 8;
+
+    if (iters <= 0) return;
+
+    st4(ex_p12 + mine, r.p12[1]);
+    st4(ex_p22 + mine, r.p22[1]);
+    __syncwarp();
+    sp_arrive(bar_b, lane0);
+    sp_primal_row<BORDER, 1>(r, k, r.p12[0], r.p22[0], gxb, gyb);  // P_1(bottom): own rows only
+
+    for (int it = 0; it < iters; ++it) {
+        sp_wait(bar_b, par_b);
+        par_b ^= 1;
+        float up12[4], up22[4];
+        ld4(ex_p12 + up, up12);
+        ld4(ex_p22 + up, up22);
+        sp_primal_row<BORDER, 0>(r, k, up12, up22, gxb, gyb);
+        st4(ex_u1 + mine, r.u1[0]);
+        st4(ex_u2 + mine, r.u2[0]);
+        __syncwarp();
+        sp_arrive(bar_a, lane0);
+
+        sp_dual_row<BORDER, 0>(r, k, r.u1[1], r.u2[1], gxb, gyb, W, H);  // own rows only: runs while the others arrive
+
+        sp_wait(bar_a, par_a);
+        par_a ^= 1;
+        float dn1[4], dn2[4];
+        ld4(ex_u1 + dn, dn1);
+        ld4(ex_u2 + dn, dn2);
+        sp_dual_row<BORDER, 1>(r, k, dn1, dn2, gxb, gyb, W, H);
+        if (it + 1 < iters) {
+            st4(ex_p12 + mine, r.p12[1]);
+            st4(ex_p22 + mine, r.p22[1]);
+            __syncwarp();
+            sp_arrive(bar_b, lane0);
+            sp_primal_row<BORDER, 1>(r, k, r.p12[0], r.p22[0], gxb, gyb);  // P_n+1(bottom): own rows only
         }
     }
 }
@@ -521,7 +637,12 @@ __device__ __forceinline__ void store_pairs(float *p, const float (&v)[4], int m
     else if (m1 == 1) p[2] = v[2];
 }
 
-template <bool ELECT, int TBOX_W, int MODE = 0>  // MODE: 0 CTA barriers, 1 two groups, 2 neighbour mbarriers
+// MODE 3 (measurement aid, tools/gpu_probe_tile_cost.py): the default kernel plus clock64 stamps of thread 0 around the
+// phases of every tile, written to this buffer (8 values per tile: before wait, after wait, after fill, before the
+// iterations, after them, after the epilogue).
+__device__ long long *g_tvl1_clock_buf = nullptr;
+
+template <bool ELECT, int TBOX_W, int MODE = 0>  // MODE: 0 CTA barriers, 1 two groups, 2 neighbour mbarriers, 3 = 0 + clocks, 4 row-skewed
 __global__ void __launch_bounds__(NT, 1)
     k_tvl1_blocked_tma(const __grid_constant__ TmaMaps maps, Plane o_u1, Plane o_u2, Plane o_p11, Plane o_p12,
                        Plane o_p21, Plane o_p22, int rows, int cols, Tvl1Scalars k, int iters, int halo, int tile,
@@ -546,31 +667,54 @@ __global__ void __launch_bounds__(NT, 1)
     const int lx = tid & 15, tr = tid >> 4;
     constexpr uint32_t kStageBytes = N_IN * TPLANE_F * sizeof(float);
 
+    // ELECT: the ten plane loads of a region are issued by ten warps (one elected lane each, each announcing its own
+    // 16 KB on the barrier), the six stores of the TMA-store epilogue by the other six.  Phase clocks had shown one lane
+    // issuing all ten loads on the critical path: ~880 cycles per tile before the first iteration, every other warp
+    // waiting for it at the first barrier.
+    constexpr int LOAD_ISSUERS = ELECT ? N_IN : 1;
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar, LOAD_ISSUERS);
         if (MODE == 2)
             for (int i = 0; i < 32; ++i) mbar_init(nb + i, 1);
+        if (MODE == 4) {
+            mbar_init(nb, NT / 32);
+            mbar_init(nb + 1, NT / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
     int t = blockIdx.x;
-    const bool issuer = ELECT ? (tid < 32 && elect_one()) : (tid == 0);
-    if (issuer && t < ntiles) {
-        const int ty = t / tiles_x, tx = t - ty * tiles_x;
-        mbar_expect_tx(bar, kStageBytes);
+    const int wid = tid >> 5;
+    const bool leader = ELECT ? elect_one() : (tid == 0);         // one fixed lane per warp (ELECT) / thread 0
+    const bool load_issuer = ELECT ? (leader && wid < N_IN) : leader;
+    const bool store_issuer = ELECT ? (leader && wid >= N_IN && wid < N_IN + N_OUT) : leader;
+    auto issue_loads = [&](int tx, int ty) {
+        const int bx = (tx * tile - halo) & ~3, by = ty * tile - halo;
+        if (ELECT) {
+            mbar_expect_tx(bar, kStageBytes / N_IN);
+            tma_load_2d(stage + wid * TPLANE_F, &maps.in[wid], bx, by, bar);
+        } else {
+            mbar_expect_tx(bar, kStageBytes);
 #pragma unroll
-        for (int pl = 0; pl < N_IN; ++pl)
-            tma_load_2d(stage + pl * TPLANE_F, &maps.in[pl], (tx * tile - halo) & ~3, ty * tile - halo, bar);
+            for (int pl = 0; pl < N_IN; ++pl) tma_load_2d(stage + pl * TPLANE_F, &maps.in[pl], bx, by, bar);
+        }
+    };
+    if (load_issuer && t < ntiles) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        issue_loads(tx, ty);
     }
     uint32_t parity = 0;
     for (; t < ntiles; t += gridDim.x) {
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         const int gx0 = tx * tile - halo, gy0 = ty * tile - halo;
         const int shift = gx0 - (gx0 & ~3);  // 0 or 2
+        long long clk[6];
+        if (MODE == 3) clk[0] = clock64();
         mbar_wait(bar, parity);
         parity ^= 1;
+        if (MODE == 3) clk[1] = clock64();
 
         Regs r;
         {
@@ -595,27 +739,33 @@ __global__ void __launch_bounds__(NT, 1)
             ldrow(8, r.p21[0], r.p21[1]);
             ldrow(9, r.p22[0], r.p22[1]);
         }
-        if (TBOX_W == R && tma_store && issuer)  // the previous tile's TMA stores have read their staging tiles
+        if (TBOX_W == R && tma_store && store_issuer)  // the previous tile's TMA stores have read their staging tiles
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();  // the staging buffer is free again
+        if (MODE == 3) clk[2] = clock64();
 
+        // No proxy fence here: the generic-proxy reads of the staging buffer completed before the barrier above (their
+        // values sit in registers); the copy engine only overwrites it (the consumer-release -> producer-load hand-off
+        // of every TMA pipeline).  The fence used to compile to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in the issuing warp.
         const int tn = t + gridDim.x;
-        if (issuer && tn < ntiles) {
+        if (load_issuer && tn < ntiles) {
             const int ny = tn / tiles_x, nx = tn - ny * tiles_x;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar, kStageBytes);
-#pragma unroll
-            for (int pl = 0; pl < N_IN; ++pl)
-                tma_load_2d(stage + pl * TPLANE_F, &maps.in[pl], (nx * tile - halo) & ~3, ny * tile - halo, bar);
+            issue_loads(nx, ny);
         }
 
         const int gxb = gx0 + 4 * lx, gyb = gy0 + 2 * tr;
         const bool border = gx0 <= 0 || gy0 <= 0 || gx0 + R >= cols || gy0 + R >= rows;
+        if (MODE == 3) clk[3] = clock64();
         if (MODE == 2) {
             if (border)
                 tile_iterate_nb<true>(r, ex, nb, par_p, par_u, iters, k, lx, tr, gxb, gyb, cols, rows);
             else
                 tile_iterate_nb<false>(r, ex, nb, par_p, par_u, iters, k, lx, tr, gxb, gyb, cols, rows);
+        } else if (MODE == 4) {
+            if (border)
+                tile_iterate_sp<true>(r, ex, nb, par_p, par_u, iters, k, lx, tr, gxb, gyb, cols, rows);
+            else
+                tile_iterate_sp<false>(r, ex, nb, par_p, par_u, iters, k, lx, tr, gxb, gyb, cols, rows);
         } else if (TWOG) {
             if (border)
                 tile_iterate_2g<true>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
@@ -625,13 +775,14 @@ __global__ void __launch_bounds__(NT, 1)
             tile_iterate<true>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
         else
             tile_iterate<false>(r, ex, iters, k, lx, tr, gxb, gyb, cols, rows);
+        if (MODE == 3) clk[4] = clock64();
 
         if (TBOX_W == R && tma_store) {
             // centre tile -> six dense 48 x 48 tiles in shared memory (over the exchange arrays) -> one TMA store each.
             // 12 STS.128 per thread replace 24 predicated STG.64 and their address arithmetic; the copy engine clips
             // edge tiles against the image.  (halo == 8 and tile == 48 here.)
             float *ot = ex;
-            if (MODE == 2) __syncthreads();  // no CTA barrier ended the last dual update: neighbours may still read ex
+            if (MODE == 2 || MODE == 4) __syncthreads();  // no CTA barrier ended the last dual update: neighbours may still read ex
             const int ox = 4 * lx - 8, oy = 2 * tr - 8;
             if (ox >= 0 && ox < OT) {
 #pragma unroll
@@ -649,10 +800,19 @@ __global__ void __launch_bounds__(NT, 1)
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
-            if (issuer) {
+            if (store_issuer) {
+                if (ELECT) {
+                    tma_store_2d(&omaps.out[wid - N_IN], ot + (wid - N_IN) * OT_F, tx * tile, ty * tile);
+                } else {
 #pragma unroll
-                for (int pl = 0; pl < N_OUT; ++pl) tma_store_2d(&omaps.out[pl], ot + pl * OT_F, tx * tile, ty * tile);
+                    for (int pl = 0; pl < N_OUT; ++pl) tma_store_2d(&omaps.out[pl], ot + pl * OT_F, tx * tile, ty * tile);
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (MODE == 3 && tid == 0 && g_tvl1_clock_buf) {
+                clk[5] = clock64();
+#pragma unroll
+                for (int i = 0; i < 6; ++i) g_tvl1_clock_buf[(size_t)t * 8 + i] = clk[i];
             }
             continue;
         }
@@ -677,7 +837,7 @@ __global__ void __launch_bounds__(NT, 1)
             }
         }
     }
-    if (TBOX_W == R && tma_store && issuer)  // the staging tiles must outlive the copy engine's reads of them
+    if (TBOX_W == R && tma_store && store_issuer)  // the staging tiles must outlive the copy engine's reads of them
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
@@ -745,8 +905,8 @@ __device__ __forceinline__ void tile_iterate_packed(RegsP &r, float4 *ex, int it
 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // thresholding constant, negated: rho * (-1/|grad|^2)
-        r.ng[i].x = -tvl1_inv_grad(r.ng[i].x);
-        r.ng[i].y = -tvl1_inv_grad(r.ng[i].y);
+        r.ng[i].x = -r.ng[i].x;
+        r.ng[i].y = -r.ng[i].y;
     }
 
     auto publish_up = [&]() {
@@ -1015,10 +1175,6 @@ __device__ __forceinline__ void tile_iterate_cluster(Regs &r, float *ex, const C
     constexpr uint32_t OFF_U1R = offsetof(ClusterGhosts, u1R), OFF_U2R = offsetof(ClusterGhosts, u2R);
     constexpr uint32_t OFF_U1D = offsetof(ClusterGhosts, u1D), OFF_U2D = offsetof(ClusterGhosts, u2D);
 
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r.gr[j][i] = tvl1_inv_grad(r.gr[j][i]);
 
     auto send_p = [&]() {  // my last column / last row of the dual variables -> right / lower neighbour
         if (role & CR_RIGHT) {
@@ -1364,7 +1520,7 @@ constexpr size_t ex_area_floats(int box_w, int mode) {
                      : (box_w == R && (size_t)N_OUT * OT_F > 4 * (size_t)EX_F ? (size_t)N_OUT * OT_F : 4 * (size_t)EX_F);
 }
 constexpr size_t smem_tma_bytes(int box_w, int mode = 0) {
-    return sizeof(float) * ((size_t)N_IN * box_w * R + ex_area_floats(box_w, mode)) + 64 + (mode == 2 ? 256 : 0);
+    return sizeof(float) * ((size_t)N_IN * box_w * R + ex_area_floats(box_w, mode)) + 64 + (mode == 2 || mode == 4 ? 256 : 0);
 }
 static_assert(smem_tma_bytes(R, 0) <= 227 * 1024 && smem_tma_bytes(R, 1) <= 227 * 1024 && smem_tma_bytes(R, 2) <= 227 * 1024,
               "TV-L1 TMA kernel: shared memory over the 227 KB limit");
@@ -1381,6 +1537,39 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
     const double bytes = 64.0 * (double)rows * cols * iters;
     const bool aligned = (halo & 3) == 0 && (tile & 3) == 0;  // every region origin is a multiple of 4
     const TmaMaps *m = static_cast<const TmaMaps *>(maps) + (aligned ? 1 : 0);
+    // measurement aid (tools/gpu_probe_tile_cost.py): run fewer iterations than the geometry was laid out for, so the
+    // per-tile cost of a pass (TMA wait, register fill, epilogue) separates from the per-iteration cost.  Results are
+    // garbage with it; never set outside that probe.
+    if (const char *dbg = getenv("B2F_DBG_TVL1_ITERS")) iters = atoi(dbg) < iters ? atoi(dbg) : iters;
+    if (aligned && halo == 8 && tma_store && !c.capturing && getenv("B2F_DBG_TVL1_CLOCKS")) {  // phase clocks of every tile
+        static long long *buf = nullptr;
+        static size_t cap = 0;
+        const size_t need = (size_t)ntiles * 8;
+        if (need > cap) {
+            cudaFree(buf);
+            cudaMalloc(&buf, need * sizeof(long long));
+            cap = need;
+            cudaMemcpyToSymbol(g_tvl1_clock_buf, &buf, sizeof(buf));
+        }
+        cudaMemsetAsync(buf, 0, need * sizeof(long long), c.stream);
+        B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R, 3>), dim3(grid), dim3(NT), smem_tma_bytes(R), *m, so.u1,
+                   so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr, *om, 1);
+        cudaStreamSynchronize(c.stream);
+        std::vector<long long> h(need);
+        cudaMemcpy(h.data(), buf, need * sizeof(long long), cudaMemcpyDeviceToHost);
+        double ph[6] = {0, 0, 0, 0, 0, 0};  // wait, fill, issue+setup, iterations, epilogue, gap to the next tile of the CTA
+        int n = 0, ngap = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const long long *q = &h[(size_t)t * 8];
+            for (int i = 0; i < 5; ++i) ph[i] += (double)(q[i + 1] - q[i]);
+            ++n;
+            if (t + grid < ntiles) { ph[5] += (double)(h[(size_t)(t + grid) * 8] - q[5]); ++ngap; }
+        }
+        fprintf(stderr, "tvl1 clocks %dx%d iters %d tiles %d: wait %.0f fill %.0f setup %.0f iterate %.0f (%.0f / iteration) "
+                        "epilogue %.0f loop-back %.0f cycles per tile\n", cols, rows, iters, ntiles, ph[0] / n, ph[1] / n,
+                ph[2] / n, ph[3] / n, iters ? ph[3] / n / iters : 0.0, ph[4] / n, ngap ? ph[5] / ngap : 0.0);
+        return;
+    }
     if (aligned)
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R>), dim3(grid), dim3(NT), smem_tma_bytes(R), *m, so.u1,
                    so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr, *om,
@@ -1423,6 +1612,22 @@ void tvl1_tmanb_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlane
     const double bytes = 64.0 * (double)rows * cols * iters;
     const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;
     B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R, 2>), dim3(grid), dim3(NT), smem_tma_bytes(R, 2), *m, so.u1,
+               so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr,
+               *out_maps(maps), (tma_store && halo == 8) ? 1 : 0);
+}
+
+// Row-skewed variant of the aligned kernel (kernel_path 12).
+void tvl1_tmasp_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                       const Tvl1Scalars &k, int iters, int num_sms, bool tma_store) {
+    const Tvl1State &so = B.s[cur ^ 1];
+    const int halo = (iters + 3) & ~3;
+    const int tile = R - 2 * halo;
+    const int tiles_x = div_up(cols, tile), tiles_y = div_up(rows, tile);
+    const int ntiles = tiles_x * tiles_y;
+    const int grid = ntiles < num_sms ? ntiles : num_sms;
+    const double bytes = 64.0 * (double)rows * cols * iters;
+    const TmaMaps *m = static_cast<const TmaMaps *>(maps) + 1;
+    B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R, 4>), dim3(grid), dim3(NT), smem_tma_bytes(R, 4), *m, so.u1,
                so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr,
                *out_maps(maps), (tma_store && halo == 8) ? 1 : 0);
 }
@@ -1541,6 +1746,12 @@ cudaError_t tvl1_blocked_init() {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_tma_bytes(R, 2));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_tma_bytes(R));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_tvl1_blocked_tma<true, R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem_tma_bytes(R, 4));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_tvl1_packed_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem_packed_bytes());

@@ -58,6 +58,9 @@ void tvl1_tma_launch_dev(Ctx &c, int cls, const void *maps, const Tvl1BlockedPla
 // Two-group variant: the two halves of the region run half an iteration apart (FP32-bound primal against SFU-bound dual).
 void tvl1_tmanb_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                        const Tvl1Scalars &k, int iters, int num_sms, bool tma_store);
+// Row-skewed variant: the thread's independent pixel row runs between a split-phase arrive and its wait.
+void tvl1_tmasp_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
+                       const Tvl1Scalars &k, int iters, int num_sms, bool tma_store);
 void tvl1_tma2g_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes &B, int cur, int rows, int cols,
                        const Tvl1Scalars &k, int iters, int num_sms);
 

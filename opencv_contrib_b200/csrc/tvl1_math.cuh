@@ -27,8 +27,8 @@ struct Tvl1Scalars {
 
 // Per-pixel constant of the thresholding step: 1/|grad I|^2, or a huge value where the reference
 // treats the gradient as zero (grad <= FLT_EPSILON), so that the clamp below degenerates to the
-// reference's sign test there.  Constant over the inner iterations of a warp: the blocked kernel
-// evaluates it once per tile.
+// reference's sign test there.  Constant over the inner iterations of a warp: the warp kernels
+// evaluate it once per pixel and store it in the `grad` plane.
 __device__ __forceinline__ float tvl1_inv_grad(float grad) { return grad > FLT_EPSILON ? rcp_approx(grad) : 1e30f; }
 
 // Thresholding step TH (tvl1flow.cu:236-262): the multiplier fi with d = fi * (Ix, Iy, gamma).

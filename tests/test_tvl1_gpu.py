@@ -46,7 +46,7 @@ def test_engine_matches_cuda_semantics_model(cuda_device, h, w, kind, seed):
         st = metrics.epe_stats(got, ref)
         assert np.isfinite(got).all() and st["max"] <= 1e-3, (path, st)
     assert alg.getStats()["launches"] > 0
-    for aux in (1, 2):                                     # tap-by-tap warp kernel / separable at 32 registers
+    for aux in (1, 2, 3):                                  # tap-by-tap warp kernel / separable at 32 and 40 registers
         alt, _ = _run(cuda_device, I0, I1, aux=aux, **kw)
         st = metrics.epe_stats(alt, ref)
         assert np.isfinite(alt).all() and st["max"] <= 1e-3, ("warp kernel variant", aux, st)
@@ -62,7 +62,7 @@ def test_blocked_kernel_bit_identical_to_unfused(cuda_device, K):
     # DSMEM ghost exchange, 2 = blocked kernel with plain loads
     import os
     # 8 = two warp groups half an iteration apart (named barriers)
-    paths = (0, 4, 5, 9, 11, 2) if os.environ.get("B2F_SKIP_CLUSTER") else (0, 4, 5, 6, 7, 8, 9, 11, 2)
+    paths = (0, 4, 5, 9, 11, 12, 2) if os.environ.get("B2F_SKIP_CLUSTER") else (0, 4, 5, 6, 7, 8, 9, 11, 12, 2)
     for path in paths:
         for graph in (0, 1):
             b, _ = _run(cuda_device, I0, I1, path=path, fused=K, graph=graph, **kw)
@@ -129,6 +129,29 @@ def test_float_input_and_initial_flow(cuda_device):
     ref = gm.calc(I0, I1, gm.TVL1Params(**kw), init_flow=init)
     got, _ = _run(cuda_device, I0, I1, init=init, **kw)
     assert metrics.epe_stats(got, ref)["max"] <= 1e-3
+
+
+def test_tiled_warp_kernel_bit_identical_to_separable(cuda_device):
+    """The default warp kernel (aux_path 0) stages the I1 window of a 64x32 tile in shared memory (TMA) and gathers the
+    taps from there; pixels whose window leaves the staged box (flow > 9 px) take the global-memory window, border pixels
+    the clamped tap loop.  Same arithmetic as the separable kernel (aux_path 3): same bits, whatever path a pixel takes."""
+    # pyramid: levels below 88x56 fall back to the separable kernel, the others tile with ragged right / bottom edges
+    I0, I1, gt = synth.make_pair(203, 277, seed=3, kind="smooth")
+    kw = dict(nscales=3, warps=3, epsilon=0.0, iterations=9)
+    a, _ = _run(cuda_device, I0, I1, aux=3, **kw)
+    b, alg = _run(cuda_device, I0, I1, aux=0, **kw)
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
+    assert alg.getStats()["launches"] > 0
+    # one level, initial flows from sub-pixel to far beyond the staged margin (and pointing out of the image)
+    rng = np.random.default_rng(7)
+    yy, xx = np.mgrid[0:203, 0:277].astype(np.float32)
+    for amp in (0.7, 6.0, 11.5, 40.0):
+        init = np.stack([amp * np.sin(xx / 37.0 + yy / 53.0), amp * np.cos(xx / 41.0 - yy / 29.0)], axis=-1).astype(np.float32)
+        init += rng.uniform(-0.5, 0.5, init.shape).astype(np.float32)
+        k1 = dict(nscales=1, warps=2, epsilon=0.0, iterations=5, useInitialFlow=True)
+        a, _ = _run(cuda_device, I0, I1, aux=3, init=init, **k1)
+        b, _ = _run(cuda_device, I0, I1, aux=0, init=init, **k1)
+        assert np.isfinite(b).all() and np.array_equal(a, b), (amp, float(np.abs(a - b).max()))
 
 
 def test_pitched_roi_inputs(cuda_device):
