@@ -311,7 +311,8 @@ __device__ __forceinline__ void warp_px_finish(int x, int y, float u1, float u2,
 // others (image border, flow beyond the margin) are only queued.  Phase 2: the CTA's queue is worked off one pixel per
 // thread.  (Handling them in place was measured first: a warp on the left / right image edge then makes 8 slow calls in
 // a row and every launch ends ~25 us late, whatever the image size.)
-__global__ void __launch_bounds__(WT_THREADS, 3)
+template <int MINB>
+__global__ void __launch_bounds__(WT_THREADS, MINB)
     k_tvl1_warp_tile(const __grid_constant__ CUtensorMap mapI1, Plane I0, Plane I1, Plane u1p, Plane u2p, Plane I1wx,
                      Plane I1wy, Plane grad, Plane rho, int rows, int cols) {
     __shared__ __align__(128) float win[WB_H * WB_W];
@@ -970,7 +971,11 @@ void Tvl1Engine::proc_one_scale(Ctx &c, int s, Plane &u3cur, bool allow_sync) {
         // reference's order (62 registers, 4 blocks / SM), 2 separable at 32 registers (8 blocks / SM), 3 separable at 40
         // registers (6 blocks / SM; the default before the tiled kernel)
         if (knobs.aux_path == 0 && warp_maps_ && cols >= WB_W && rows >= WB_H)  // I1 window staged by the copy engine
-            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_tile, dim3(div_up(cols, WT_W), div_up(rows, WT_H)),
+            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_tile<4>, dim3(div_up(cols, WT_W), div_up(rows, WT_H)),
+                       dim3(WT_THREADS), 0, warp_maps_[s], lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy, T.grad, T.rho_c, rows,
+                       cols);
+        else if (knobs.aux_path == 4 && warp_maps_ && cols >= WB_W && rows >= WB_H)  // same at 77 registers, 3 blocks / SM
+            B2F_LAUNCH(c, CLS_WARP, 32.0 * npx, k_tvl1_warp_tile<3>, dim3(div_up(cols, WT_W), div_up(rows, WT_H)),
                        dim3(WT_THREADS), 0, warp_maps_[s], lv.I0, lv.I1, T.u1, T.u2, T.I1wx, T.I1wy, T.grad, T.rho_c, rows,
                        cols);
         else if (knobs.aux_path == 1)
