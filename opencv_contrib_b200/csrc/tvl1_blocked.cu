@@ -691,6 +691,11 @@ __global__ void __launch_bounds__(NT, 1)
     }
     __syncthreads();
 
+    // bit 1 of tma_store: walk the tiles from the last to the first.  Passes alternate direction, so a pass begins where the
+    // previous kernel of the stream ended: the first region of every CTA -- the cold load nothing hides -- is then the data
+    // written (or read) last, i.e. still in L2.
+    const bool rev = (tma_store & 2) != 0;
+    tma_store &= 1;
     int t = blockIdx.x;
     auto issue_loads = [&](int tx, int ty) {
         const int bx = (tx * tile - halo) & ~3, by = ty * tile - halo;
@@ -704,12 +709,14 @@ __global__ void __launch_bounds__(NT, 1)
         }
     };
     if (load_issuer && t < ntiles) {
-        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int tt = rev ? ntiles - 1 - t : t;
+        const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
         issue_loads(tx, ty);
     }
     uint32_t parity = 0;
     for (; t < ntiles; t += gridDim.x) {
-        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int tt = rev ? ntiles - 1 - t : t;
+        const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
         const int gx0 = tx * tile - halo, gy0 = ty * tile - halo;
         const int shift = gx0 - (gx0 & ~3);  // 0 or 2
         long long clk[6];
@@ -751,7 +758,8 @@ __global__ void __launch_bounds__(NT, 1)
         // of every TMA pipeline).  The fence used to compile to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in the issuing warp.
         const int tn = t + gridDim.x;
         if (load_issuer && tn < ntiles) {
-            const int ny = tn / tiles_x, nx = tn - ny * tiles_x;
+            const int tnn = rev ? ntiles - 1 - tn : tn;
+            const int ny = tnn / tiles_x, nx = tnn - ny * tiles_x;
             issue_loads(nx, ny);
         }
 
@@ -1542,6 +1550,10 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
     const int grid = ntiles < num_sms ? ntiles : num_sms;
     const double bytes = 64.0 * (double)rows * cols * iters;
     const bool aligned = (halo & 3) == 0 && (tile & 3) == 0;  // every region origin is a multiple of 4
+    // passes alternate their walking direction (see the kernel); `cur` flips with every pass and is 0 for the pass that
+    // follows the warp kernel, which ended at the bottom of the image
+    static const bool norev = getenv("B2F_DBG_TVL1_NOREV") != nullptr;
+    const bool reverse = !norev && cur == 0;
     const TmaMaps *m = static_cast<const TmaMaps *>(maps) + (aligned ? 1 : 0);
     // measurement aid (tools/gpu_probe_tile_cost.py): run fewer iterations than the geometry was laid out for, so the
     // per-tile cost of a pass (TMA wait, register fill, epilogue) separates from the per-iteration cost.  Results are
@@ -1579,7 +1591,7 @@ void tvl1_tma_launch(Ctx &c, int cls, const void *maps, const Tvl1BlockedPlanes 
     if (aligned)
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, R>), dim3(grid), dim3(NT), smem_tma_bytes(R), *m, so.u1,
                    so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters, halo, tile, tiles_x, ntiles, nullptr, *om,
-                   (tma_store && halo == 8) ? 1 : 0);
+                   ((tma_store && halo == 8) ? 1 : 0) | (reverse ? 2 : 0));
     else if (elect)
         B2F_LAUNCH(c, cls, bytes, (k_tvl1_blocked_tma<true, TBOX_WIDE>), dim3(grid), dim3(NT),
                    smem_tma_bytes(TBOX_WIDE), *m, so.u1, so.u2, so.p11, so.p12, so.p21, so.p22, rows, cols, k, iters,
