@@ -167,7 +167,10 @@ typedef enum b2f_param_id {
                                      TMA kernel, 6 / 7 = 2x2 / 2x1-cluster kernels, 8 = two warp groups half an
                                      iteration apart, 9 = warps synchronise with their neighbours through mbarriers
                                      (11 = 9 with the TMA-store epilogue), 12 = row-skewed iterations behind
-                                     split-phase mbarriers.  All bit-identical; 0 is the fastest.                  */
+                                     split-phase mbarriers.  All bit-identical; 0 is the fastest.
+                                     Brox: 0 = register-resident solver, one prepare + one solver launch per inner
+                                     step, 1 = one launch per half sweep, 2 = shared-memory solver, 3 = all inner steps
+                                     of a level in one cooperative launch (measured slower).  All bit-identical.  */
     B2F_ENGINE_AUX_PATH = 903     /* variant of the secondary kernels.  TV-L1 warp: 0 = tiled kernel (I1 window of a
                                      64x32 tile staged in shared memory by TMA), 1 = tap-by-tap kernel (accumulation
                                      in the reference's order), 2 / 3 = separable kernel at 32 / 40 registers; 0, 2

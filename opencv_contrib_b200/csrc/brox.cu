@@ -18,7 +18,9 @@
 // 1 prepare (104 B/px), 2 derivatives, 3 pyramid (supersample / bicubic prolongation / add).
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -219,40 +221,55 @@ __global__ void __launch_bounds__(256) k_brox_warp_terms(BroxLevelPlanes P, int 
 // prepare_sor_stage_1 + stage_2 fused (NB:340-473).  The smoothness diffusivities are computed once per cell
 // edge from a shared tile (each is needed by the two cells it separates) instead of four 24-load evaluations
 // per pixel; the data term samples the warped image and its derivatives in software.
-__global__ void __launch_bounds__(PB_X *PB_Y) k_brox_prepare(BroxLevelPlanes P, int h, int w, float alpha, float gamma) {
-    __shared__ PrepTile T;
-    __shared__ float s_sx[PB_Y][PB_X + 1];   // sx at tile columns 0..32
-    __shared__ float s_sy[PB_Y + 1][PB_X];   // sy at tile rows 0..8
-    const int tid = threadIdx.y * PB_X + threadIdx.x;
-    const int gx0 = blockIdx.x * PB_X, gy0 = blockIdx.y * PB_Y;
-    for (int t = tid; t < PT_W * PT_H; t += PB_X * PB_Y) {
-        const int ry = t / PT_W, rx = t - ry * PT_W;
-        const int y = mirror_load(gy0 - 1 + ry, h), x = mirror_load(gx0 - 1 + rx, w);
-        T.u[ry][rx] = P.u.at(y, x);
-        T.du[ry][rx] = P.du.at(y, x);
-        T.v[ry][rx] = P.v.at(y, x);
-        T.dv[ry][rx] = P.dv.at(y, x);
+// One 32 x 8 chunk worked by 256 threads (tid = ty * 32 + tx); every thread of the CTA must call it (two barriers),
+// `active` = the chunk exists.  CG: read what other CTAs of the SAME launch wrote (du, dv) through L2 (ld.global.cg) --
+// the cooperative level kernel below runs many inner iterations in one launch, and L1 is not coherent.
+template <bool CG>
+__device__ __forceinline__ float brox_ld(const Plane &p, int y, int x) {
+    return CG ? __ldcg(&p.at(y, x)) : p.at(y, x);
+}
+struct PrepShared {
+    PrepTile T;
+    float sx[PB_Y][PB_X + 1];   // sx at tile columns 0..32
+    float sy[PB_Y + 1][PB_X];   // sy at tile rows 0..8
+};
+template <bool CG>
+__device__ __forceinline__ void brox_prepare_chunk(const BroxLevelPlanes &P, int h, int w, float alpha, float gamma, int gx0,
+                                                   int gy0, int tid, PrepShared &S, bool active) {
+    PrepTile &T = S.T;
+    const int tx = tid & (PB_X - 1), ty = tid / PB_X;
+    if (active) {
+        for (int t = tid; t < PT_W * PT_H; t += PB_X * PB_Y) {
+            const int ry = t / PT_W, rx = t - ry * PT_W;
+            const int y = mirror_load(gy0 - 1 + ry, h), x = mirror_load(gx0 - 1 + rx, w);
+            T.u[ry][rx] = P.u.at(y, x);
+            T.du[ry][rx] = brox_ld<CG>(P.du, y, x);
+            T.v[ry][rx] = P.v.at(y, x);
+            T.dv[ry][rx] = brox_ld<CG>(P.dv, y, x);
+        }
     }
     __syncthreads();
     constexpr int N_SX = PB_Y * (PB_X + 1), N_SY = (PB_Y + 1) * PB_X;
-    for (int t = tid; t < N_SX + N_SY; t += PB_X * PB_Y) {
-        if (t < N_SX) {
-            const int ry = t / (PB_X + 1), rx = t - ry * (PB_X + 1);
-            const int gy = gy0 + ry, gx = gx0 + rx;
-            // sx = 0 at i = 0 (NB:396) and beyond the image (stage 2 treats it as zero, NB:440-452)
-            s_sx[ry][rx] = (gx == 0 || gx >= w || gy >= h) ? 0.f : brox_sx(T, ry + 1, rx + 1);
-        } else {
-            const int q = t - N_SX;
-            const int ry = q / PB_X, rx = q - ry * PB_X;
-            const int gy = gy0 + ry, gx = gx0 + rx;
-            s_sy[ry][rx] = (gy == 0 || gy >= h || gx >= w) ? 0.f : brox_sy(T, ry + 1, rx + 1);
+    if (active) {
+        for (int t = tid; t < N_SX + N_SY; t += PB_X * PB_Y) {
+            if (t < N_SX) {
+                const int ry = t / (PB_X + 1), rx = t - ry * (PB_X + 1);
+                const int gy = gy0 + ry, gx = gx0 + rx;
+                // sx = 0 at i = 0 (NB:396) and beyond the image (stage 2 treats it as zero, NB:440-452)
+                S.sx[ry][rx] = (gx == 0 || gx >= w || gy >= h) ? 0.f : brox_sx(T, ry + 1, rx + 1);
+            } else {
+                const int q = t - N_SX;
+                const int ry = q / PB_X, rx = q - ry * PB_X;
+                const int gy = gy0 + ry, gx = gx0 + rx;
+                S.sy[ry][rx] = (gy == 0 || gy >= h || gx >= w) ? 0.f : brox_sy(T, ry + 1, rx + 1);
+            }
         }
     }
     __syncthreads();
 
-    const int ig = gx0 + threadIdx.x, jg = gy0 + threadIdx.y;
-    if (ig >= w || jg >= h) return;
-    const float du = T.du[threadIdx.y + 1][threadIdx.x + 1], dv = T.dv[threadIdx.y + 1][threadIdx.x + 1];
+    const int ig = gx0 + tx, jg = gy0 + ty;
+    if (!active || ig >= w || jg >= h) return;
+    const float du = T.du[ty + 1][tx + 1], dv = T.dv[ty + 1][tx + 1];
     const float Iz = P.wIz.at(jg, ig), Ix = P.wIx.at(jg, ig), Ixz = P.wIxz.at(jg, ig), Ixy = P.wIxy.at(jg, ig);
     const float Ixx = P.wIxx.at(jg, ig), Iy = P.wIy.at(jg, ig), Iyz = P.wIyz.at(jg, ig), Iyy = P.wIyy.at(jg, ig);
     const float q0 = Iz + Ix * du + Iy * dv;
@@ -261,8 +278,8 @@ __global__ void __launch_bounds__(PB_X *PB_Y) k_brox_prepare(BroxLevelPlanes P, 
     float data_term = 0.5f * rsqrtf(q0 * q0 + gamma * (q1 * q1 + q2 * q2) + EPS2);
     data_term /= alpha;
 
-    const float sx = s_sx[threadIdx.y][threadIdx.x], sxr = s_sx[threadIdx.y][threadIdx.x + 1];
-    const float sy = s_sy[threadIdx.y][threadIdx.x], syu = s_sy[threadIdx.y + 1][threadIdx.x];
+    const float sx = S.sx[ty][tx], sxr = S.sx[ty][tx + 1];
+    const float sy = S.sy[ty][tx], syu = S.sy[ty + 1][tx];
 
     P.num_dudv.at(jg, ig) = data_term * (Ix * Iy + gamma * Ixy * (Ixx + Iyy));
     P.num_u.at(jg, ig) = data_term * (Ix * Iz + gamma * (Ixx * Ixz + Ixy * Iyz));
@@ -274,6 +291,12 @@ __global__ void __launch_bounds__(PB_X *PB_Y) k_brox_prepare(BroxLevelPlanes P, 
     const float dsum = sx + sxr + sy + syu;
     P.inv_u.at(jg, ig) = 1.0f / (den_u + dsum);
     P.inv_v.at(jg, ig) = 1.0f / (den_v + dsum);
+}
+
+__global__ void __launch_bounds__(PB_X *PB_Y) k_brox_prepare(BroxLevelPlanes P, int h, int w, float alpha, float gamma) {
+    __shared__ PrepShared S;
+    brox_prepare_chunk<false>(P, h, w, alpha, gamma, blockIdx.x * PB_X, blockIdx.y * PB_Y, threadIdx.y * PB_X + threadIdx.x, S,
+                              true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -500,17 +523,18 @@ __device__ __forceinline__ void brox_half_sweep(SorRegs (&c)[4][2], const float4
     xV[(ry0 + 3) * SR + rx0 + cpB] = c[3][cpB].V;
 }
 
-__global__ void __launch_bounds__(S_THREADS, 1)
-    k_brox_sor_reg(BroxLevelPlanes P, Plane du_out, Plane dv_out, int h, int w, float omega, int iters, int halo,
-                   int tile) {
-    extern __shared__ float4 sor4[];
+// One 64 x 64 region: load, `iters` full iterations in registers, store the centre tile.  (bx, by) = region index.
+// CG: operands written by other CTAs of the same launch (du, dv and everything k_brox_prepare produces) are read through L2.
+template <bool CG>
+__device__ __forceinline__ void brox_sor_region(const BroxLevelPlanes &P, Plane du_out, Plane dv_out, int h, int w, float omega,
+                                                int iters, int halo, int tile, int bx, int by, float4 *sor4) {
     float4 *sS = sor4;                 // [row][colour-parity][k] : s_l, s_r, s_u, s_d
     float4 *sN = sor4 + SR * SR;       // same layout            : num_u, num_v, num_dudv, omega * inv_u
     float *xU = reinterpret_cast<float *>(sor4 + 2 * SR * SR);  // boundary-row exchange, [row][col]
     float *xV = xU + SR * SR;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rx0 = 2 * lane, ry0 = 4 * warp;
-    const int gx0 = blockIdx.x * tile - halo, gy0 = blockIdx.y * tile - halo;  // both even
+    const int gx0 = bx * tile - halo, gy0 = by * tile - halo;  // both even
 
     SorRegs c[4][2];
 #pragma unroll
@@ -523,22 +547,22 @@ __global__ void __launch_bounds__(S_THREADS, 1)
             float4 S = make_float4(0.f, 0.f, 0.f, 0.f), N = make_float4(0.f, 0.f, 0.f, 0.f);
             m.du = m.dv = m.u = m.v = m.usum = m.vsum = m.w_v = 0.f;
             if (in) {
-                m.du = P.du.at(gy, gx);
-                m.dv = P.dv.at(gy, gx);
+                m.du = brox_ld<CG>(P.du, gy, gx);
+                m.dv = brox_ld<CG>(P.dv, gy, gx);
                 m.u = P.u.at(gy, gx);
                 m.v = P.v.at(gy, gx);
-                S.x = P.sx.at(gy, gx);
-                S.w = P.sy.at(gy, gx);
-                S.y = gx < w - 1 ? P.sx.at(gy, gx + 1) : 0.0f;
-                S.z = gy < h - 1 ? P.sy.at(gy + 1, gx) : 0.0f;
+                S.x = brox_ld<CG>(P.sx, gy, gx);
+                S.w = brox_ld<CG>(P.sy, gy, gx);
+                S.y = gx < w - 1 ? brox_ld<CG>(P.sx, gy, gx + 1) : 0.0f;
+                S.z = gy < h - 1 ? brox_ld<CG>(P.sy, gy + 1, gx) : 0.0f;
                 const float ssum = brox_ssum(S.x, S.y, S.z, S.w);
                 m.usum = __fmul_rn(m.u, ssum);
                 m.vsum = __fmul_rn(m.v, ssum);
-                N.x = P.num_u.at(gy, gx);
-                N.y = P.num_v.at(gy, gx);
-                N.z = P.num_dudv.at(gy, gx);
-                N.w = __fmul_rn(omega, P.inv_u.at(gy, gx));
-                m.w_v = __fmul_rn(omega, P.inv_v.at(gy, gx));
+                N.x = brox_ld<CG>(P.num_u, gy, gx);
+                N.y = brox_ld<CG>(P.num_v, gy, gx);
+                N.z = brox_ld<CG>(P.num_dudv, gy, gx);
+                N.w = __fmul_rn(omega, brox_ld<CG>(P.inv_u, gy, gx));
+                m.w_v = __fmul_rn(omega, brox_ld<CG>(P.inv_v, gy, gx));
             }
             m.U = __fadd_rn(m.u, m.du);
             m.V = __fadd_rn(m.v, m.dv);
@@ -581,6 +605,66 @@ __global__ void __launch_bounds__(S_THREADS, 1)
             du_out.at(gy, gx) = c[r][q].du;
             dv_out.at(gy, gx) = c[r][q].dv;
         }
+    }
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+    k_brox_sor_reg(BroxLevelPlanes P, Plane du_out, Plane dv_out, int h, int w, float omega, int iters, int halo,
+                   int tile) {
+    extern __shared__ float4 sor4[];
+    brox_sor_region<false>(P, du_out, dv_out, h, w, omega, iters, halo, tile, blockIdx.x, blockIdx.y, sor4);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cooperative level kernel: ALL inner iterations of a level in one launch -- per inner iteration the prepare pass over
+// the level's 32 x 8 chunks (two at a time per CTA), a grid-wide barrier, the register-resident solver on the CTA's
+// region (all solver iterations), a grid-wide barrier.  For the levels whose solver takes every iteration in one launch
+// (13 of the 19 levels of a 720p pyramid; they are bound by launch floors, not by work) this replaces 2 x inner launches
+// and their gaps.  Opt-in (kernel_path 3): measured slower than the launch-per-step graph, see BroxEngine::solve.  Launched with cudaLaunchCooperativeKernel (co-residency is what makes the spin barrier legal); the
+// barrier counter is zeroed by a memset node in front of every launch.  Same device functions as the stand-alone kernels:
+// bit-identical to them.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void brox_grid_barrier(unsigned *counter, unsigned nblocks, unsigned &epoch) {
+    __syncthreads();
+    ++epoch;
+    if (threadIdx.x == 0) {
+        __threadfence();  // this CTA's stores before its arrival
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * nblocks;
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1)
+    k_brox_level_coop(BroxLevelPlanes P, Plane dun, Plane dvn, int h, int w, float alpha, float gamma, float omega, int inner,
+                      int iters, int halo, int tile, int tiles_x, unsigned *barrier) {
+    extern __shared__ float4 sor4[];
+    __shared__ PrepShared PS[2];
+    const int tid = threadIdx.x, half = tid >> 8, t256 = tid & 255;
+    const int chunks_x = (w + PB_X - 1) / PB_X, chunks_y = (h + PB_Y - 1) / PB_Y, nchunks = chunks_x * chunks_y;
+    const int by = blockIdx.x / tiles_x, bx = blockIdx.x - by * tiles_x;
+    unsigned epoch = 0;
+    Plane cdu = P.du, cdv = P.dv, ndu = dun, ndv = dvn;
+    for (int in = 0; in < inner; ++in) {
+        BroxLevelPlanes Q = P;
+        Q.du = cdu;
+        Q.dv = cdv;
+        for (int c0 = 2 * blockIdx.x; c0 < nchunks; c0 += 2 * gridDim.x) {  // uniform trip count over the CTA
+            const int c = c0 + half;
+            const bool active = c < nchunks;
+            const int cy = active ? c / chunks_x : 0, cx = active ? c - cy * chunks_x : 0;
+            brox_prepare_chunk<true>(Q, h, w, alpha, gamma, cx * PB_X, cy * PB_Y, t256, PS[half], active);
+            __syncthreads();  // the tiles are reused by the next round
+        }
+        brox_grid_barrier(barrier, gridDim.x, epoch);
+        brox_sor_region<true>(Q, ndu, ndv, h, w, omega, iters, halo, tile, bx, by, sor4);
+        Plane t1 = cdu; cdu = ndu; ndu = t1;
+        Plane t2 = cdv; cdv = ndv; ndv = t2;
+        brox_grid_barrier(barrier, gridDim.x, epoch);
     }
 }
 
@@ -664,6 +748,9 @@ private:
     enum { S_IX = 0, S_IXX, S_IX0, S_IY, S_IYY, S_IY0, S_IXY, S_U, S_V, S_UN, S_VN, S_DU, S_DV, S_DUN, S_DVN, S_SX, S_SY,
            S_INVU, S_INVV, S_NDUDV, S_WIZ, S_WIX, S_WIXZ, S_WIXY, S_WIXX, S_WIY, S_WIYZ, S_WIYY, S_COUNT };
     float *extra_[2] = {};  // num_u, num_v
+    unsigned *coop_barrier_ = nullptr;  // arrival counter of the cooperative level kernel (zeroed before every launch)
+    int coop_max_blocks_ = -1;          // co-resident CTAs of k_brox_level_coop on this device (0: cooperative launch unsupported)
+    bool coop_ok(int blocks);
     int final_ui_ = 0;      // which (u, v) buffer pair holds the result (fixed by the level count)
 
     cudaGraphExec_t graph_exec_ = nullptr;
@@ -713,9 +800,11 @@ size_t BroxEngine::layout(int rows, int cols, bool counting, Layout &L) {
     }
     for (int i = 0; i < S_COUNT; ++i) L.shared[i] = A.plane(rows, cols).p;
     float *a = A.plane(rows, cols).p, *b = A.plane(rows, cols).p;
+    unsigned *bar = static_cast<unsigned *>(A.bytes(256));
     if (!counting) {
         extra_[0] = a;
         extra_[1] = b;
+        coop_barrier_ = bar;
     }
     return A.used();
 }
@@ -730,6 +819,23 @@ cudaError_t BroxEngine::ensure_workspace(int rows, int cols) {
     if (e != cudaSuccess) return e;
     layout(rows, cols, false, L_);
     return cudaSuccess;
+}
+
+bool BroxEngine::coop_ok(int blocks) {
+    if (coop_max_blocks_ < 0) {
+        coop_max_blocks_ = 0;
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        const size_t smem = sizeof(float) * 10 * SR * SR;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaFuncSetAttribute(k_brox_level_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_brox_level_coop, S_THREADS, smem) == cudaSuccess)
+            coop_max_blocks_ = per_sm * sms;
+        cudaGetLastError();
+        if (getenv("B2F_BROX_NO_COOP")) coop_max_blocks_ = 0;
+    }
+    return blocks > 0 && blocks <= coop_max_blocks_;
 }
 
 void BroxEngine::solve(Ctx &c) {
@@ -775,39 +881,70 @@ void BroxEngine::solve(Ctx &c) {
         B2F_LAUNCH(c, CLS_DERIV, 24.0 * npx, k_brox_deriv1, grid, block, 0, T.I0, T.I1, T.Ix0, T.Iy0, T.Ix, T.Iy, h, w);
         B2F_LAUNCH(c, CLS_DERIV, 20.0 * npx, k_brox_deriv2, grid, block, 0, T.Ix, T.Iy, T.Ixx, T.Iyy, T.Ixy, h, w);
         B2F_LAUNCH(c, CLS_PREP, 76.0 * npx, k_brox_warp_terms, grid, block, 0, T, h, w);
-        for (int in = 0; in < P.inner_iterations; ++in) {
+        const float omega = 1.99f;  // NB:914
+        // fused path: up to 12 full iterations per launch (all of them when the level fits one region).
+        // A CTA reads its halo from global memory that neighbouring CTAs overwrite with their centre
+        // tiles at the end, so launches ping-pong between (du, dv) and (dun, dvn).
+        const bool single = w <= SR && h <= SR;  // whole level in one region: no halo, one launch
+        // iterations fused per launch: more iterations = fewer launches but a wider halo (smaller tile,
+        // more CTAs).  Small and mid levels are latency-bound (one wave), so they take all iterations in
+        // one launch; large levels keep the tile big.  Cost model in microseconds: fill ~3, half sweep
+        // ~0.35, launch gap ~2, per wave of 148 CTAs.
+        int it_best = 5;
+        if (!single && knobs.fused_iters > 0) {
+            it_best = knobs.fused_iters;
+        } else if (!single) {
+            double best = 1e30;
+            for (int cand = 1; cand <= 12 && cand <= P.solver_iterations; ++cand) {
+                const int t = SR - 4 * cand;
+                if (t < 8) break;
+                const int launches = div_up(P.solver_iterations, cand);
+                const double waves = std::ceil((double)div_up(w, t) * div_up(h, t) / 148.0);
+                const double cost = launches * (waves * (3.0 + 0.7 * cand) + 2.0);
+                if (cost < best) {
+                    best = cost;
+                    it_best = cand;
+                }
+            }
+        }
+        if (it_best > 13) it_best = 13;
+
+        // kernel_path 3 (opt-in): whole level in ONE cooperative launch when every solver iteration of an inner step fits
+        // one launch and all its regions are co-resident.  Measured on B200 at 720p (10, 77, 10): 337 instead of 584
+        // launches per pair, bit-identical, but 6.90 instead of 6.05 ms -- two software grid barriers per inner step (fence +
+        // atomic + acquire polling, ~3 us each) and the cooperative launches cost more than the ~1.5 us a graph leaves between
+        // two kernel nodes, and the prepare pass runs on the solver's CTAs only.  The default stays launch-per-step.
+        const int it1 = single ? P.solver_iterations : std::min(P.solver_iterations, it_best);
+        const int halo1 = single ? 0 : 2 * it1, tile1 = single ? SR : SR - 2 * halo1;
+        const int tx1 = single ? 1 : div_up(w, tile1), ty1 = single ? 1 : div_up(h, tile1);
+        const bool use_coop = knobs.kernel_path == 3 && it1 == P.solver_iterations && P.solver_iterations > 0 &&
+                              P.inner_iterations > 0 && coop_ok(tx1 * ty1);
+        if (use_coop) {
+            c.check(cudaMemsetAsync(coop_barrier_, 0, sizeof(unsigned), c.stream));
+            if (c.ok()) {
+                c.pre(CLS_SOR, (52.0 * it1 + 104.0) * npx * P.inner_iterations);
+                BroxLevelPlanes Q = T;
+                float alpha_f = static_cast<float>(P.alpha), gamma_f = static_cast<float>(P.gamma), omega_f = omega;
+                int h_ = h, w_ = w, inner_ = P.inner_iterations, iters_ = it1, halo_ = halo1, tile_ = tile1, tx_ = tx1;
+                unsigned *bar_ = coop_barrier_;
+                void *args[] = {&Q, &dun, &dvn, &h_, &w_, &alpha_f, &gamma_f, &omega_f, &inner_, &iters_, &halo_, &tile_,
+                                &tx_, &bar_};
+                c.check(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k_brox_level_coop), dim3(tx1 * ty1),
+                                                    dim3(S_THREADS), args, sor_reg_smem, c.stream));
+                c.post(CLS_SOR);
+                c.stats->iterations_run += it1 * P.inner_iterations;
+            }
+            if (P.inner_iterations & 1) {  // odd number of solver passes: the result sits in the spare pair
+                Plane t1 = T.du; T.du = dun; dun = t1;
+                Plane t2 = T.dv; T.dv = dvn; dvn = t2;
+            }
+        }
+        for (int in = 0; in < P.inner_iterations && !use_coop; ++in) {
             B2F_LAUNCH(c, CLS_PREP, 104.0 * npx, k_brox_prepare, grid, block, 0, T, h, w, static_cast<float>(P.alpha),
                        static_cast<float>(P.gamma));
-            const float omega = 1.99f;  // NB:914
             if (knobs.kernel_path != 1) {
-                // fused path: up to 5 full iterations per launch (all of them when the level fits one region).
-                // A CTA reads its halo from global memory that neighbouring CTAs overwrite with their centre
-                // tiles at the end, so launches ping-pong between (du, dv) and (dun, dvn).
                 int left = P.solver_iterations;
-                const bool single = w <= SR && h <= SR;  // whole level in one region: no halo, one launch
                 Plane cdu = T.du, cdv = T.dv, ndu = dun, ndv = dvn;
-                // iterations fused per launch: more iterations = fewer launches but a wider halo (smaller tile,
-                // more CTAs).  Small and mid levels are latency-bound (one wave), so they take all iterations in
-                // one launch; large levels keep the tile big.  Cost model in microseconds: fill ~3, half sweep
-                // ~0.35, launch gap ~2, per wave of 148 CTAs.
-                int it_best = 5;
-                if (!single && knobs.fused_iters > 0) {
-                    it_best = knobs.fused_iters;
-                } else if (!single) {
-                    double best = 1e30;
-                    for (int cand = 1; cand <= 12 && cand <= P.solver_iterations; ++cand) {
-                        const int t = SR - 4 * cand;
-                        if (t < 8) break;
-                        const int launches = div_up(P.solver_iterations, cand);
-                        const double waves = std::ceil((double)div_up(w, t) * div_up(h, t) / 148.0);
-                        const double cost = launches * (waves * (3.0 + 0.7 * cand) + 2.0);
-                        if (cost < best) {
-                            best = cost;
-                            it_best = cand;
-                        }
-                    }
-                }
-                if (it_best > 13) it_best = 13;
                 while (left > 0) {
                     const int it = single ? left : (left < it_best ? left : it_best);
                     const int halo = single ? 0 : 2 * it;

@@ -43,20 +43,29 @@ def test_brox_matches_model(cuda_device, h, w, kind):
 @pytest.mark.parametrize("h,w,solver", [(150, 203, 7), (61, 64, 10), (300, 417, 10)])
 def test_brox_fused_sor_bit_identical_to_half_sweep_kernels(cuda_device, h, w, solver):
     """kernel_path=1 runs one launch per red/black half sweep (the reference's shape); path 2 fuses up to 5
-    iterations per launch in shared memory; the default path keeps the cells in registers.  Same arithmetic,
-    same order (brox_sor_cell) -> same bits, including levels that fit one region and odd sizes."""
+    iterations per launch in shared memory; the default path (0) keeps the cells in registers, one prepare + one solver
+    launch per inner step; path 3 additionally runs ALL inner steps of a level in one cooperative launch (grid-wide barriers
+    between the prepare and solver phases) wherever the level's regions are co-resident.  Same arithmetic, same order
+    (brox_sor_cell) -> same bits, including levels that fit one region and odd sizes; inner = 3 and 4 cover both parities
+    of the (du, dv) ping-pong."""
     import torch
     import opencv_contrib_b200 as ocb
     I0, I1, _ = synth.make_pair(h, w, seed=7, kind="smooth", dtype="f32")
     d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
-    outs = []
-    for path in (0, 1, 2):
-        alg = ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, 3, 77, solver)
-        alg.setEngineOption("kernel_path", path)
-        outs.append(alg.calc(d0, d1).cpu().numpy())
-    assert np.isfinite(outs[0]).all()
-    assert np.array_equal(outs[0], outs[1]), float(np.abs(outs[0] - outs[1]).max())
-    assert np.array_equal(outs[2], outs[1]), float(np.abs(outs[2] - outs[1]).max())
+    for inner in (3, 4):
+        outs, launches = [], []
+        for path in (0, 1, 2, 3):
+            alg = ocb.BroxOpticalFlow_create(0.197, 50.0, 0.8, inner, 77, solver)
+            alg.setEngineOption("kernel_path", path)
+            outs.append(alg.calc(d0, d1).cpu().numpy())
+            again = alg.calc(d0, d1).cpu().numpy()          # graph replay (barrier counter zeroed by its memset node)
+            assert np.array_equal(again, outs[-1]), path
+            launches.append(alg.getStats()["launches"])
+        assert np.isfinite(outs[0]).all()
+        assert np.array_equal(outs[0], outs[1]), (inner, float(np.abs(outs[0] - outs[1]).max()))
+        assert np.array_equal(outs[2], outs[1]), (inner, float(np.abs(outs[2] - outs[1]).max()))
+        assert np.array_equal(outs[3], outs[1]), (inner, float(np.abs(outs[3] - outs[1]).max()))
+        assert launches[3] < launches[0], launches        # the cooperative level kernel replaced launches
 
 
 def test_brox_reference_test_parameters_recover_motion(cuda_device):
