@@ -285,6 +285,112 @@ __global__ void __launch_bounds__(256) k_farn_polyexp(Plane s0, Plane s1, Stack5
     dst.at(4, y, x) = b6 * T.ig55;
 }
 
+// Register-blocked variant (round 2, the default): the kernel above executes ~270 instructions per pixel -- every output of
+// the vertical pass issues its own 2N+1 loads, the second round of its 32-lane column loop is two thirds empty (42 columns),
+// the horizontal pass reads 6N+3 scalars from shared memory per pixel -- and takes ~100 us for the two 1080p frames, 6x its
+// 100 MB of traffic.  Here one block = 64 x 32 pixels; a vertical task is (column, 8-row segment): 8+2N loads feed 8 outputs
+// from a register window; a horizontal task is (row, 4 pixels): 4 (N = 5) or 5 (N = 7) LDS.128 per moment feed 4 outputs, and
+// the five results leave as float4.  Same expressions in the same order per output: bit-identical (tested; aux_path 6 keeps
+// the kernel above).
+template <int N>
+__global__ void __launch_bounds__(256) k_farn_polyexp_fast(Plane s0, Plane s1, Stack5 r0, Stack5 r1, int rows, int cols,
+                                                           PolyTabs T) {
+    constexpr int TW = 64, TH = 32, NC = TW + 2 * N, SW = (NC + 3) & ~3, SEG = 8, WIN = SEG + 2 * N;
+    constexpr int HW = 4 + 2 * N, HV = (HW + 3) / 4;  // horizontal window (floats / float4s)
+    __shared__ __align__(16) float sm[3][TH][SW];
+    const Plane src = blockIdx.z ? s1 : s0;
+    const Stack5 dst = blockIdx.z ? r1 : r0;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+
+    for (int task = tid; task < NC * (TH / SEG); task += 256) {
+        const int seg = task / NC, i = task - seg * NC;
+        const int ys = y0 + seg * SEG;
+        if (ys >= rows) continue;
+        const int xc = clampi(x0 + i - N, 0, cols - 1);
+        float v[WIN];
+        if (ys - N >= 0 && ys - N + WIN <= rows) {
+            const float *p = &src.at(ys - N, xc);
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) {
+                v[q] = __ldg(p);
+                p += src.pitch;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) v[q] = __ldg(&src.at(clampi(ys - N + q, 0, rows - 1), xc));
+        }
+#pragma unroll
+        for (int o = 0; o < SEG; ++o) {
+            float a0 = v[o + N] * T.g[0], a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const float t0 = v[o + N - k];
+                const float t1 = v[o + N + k];
+                a0 += T.g[k] * (t0 + t1);
+                a1 += T.xg[k] * (t1 - t0);
+                a2 += T.xxg[k] * (t0 + t1);
+            }
+            sm[0][seg * SEG + o][i] = a0;
+            sm[1][seg * SEG + o][i] = a1;
+            sm[2][seg * SEG + o][i] = a2;
+        }
+    }
+    __syncthreads();
+
+    for (int task = tid; task < TH * (TW / 4); task += 256) {
+        const int r = task / (TW / 4), q = task - r * (TW / 4);
+        const int y = y0 + r, x = x0 + 4 * q;
+        if (y >= rows || x >= cols) continue;
+        float w0[4 * HV], w1[4 * HV], w2[4 * HV];  // window columns 4q .. 4q + 4 HV - 1 (centre of pixel e at e + N)
+#pragma unroll
+        for (int c = 0; c < HV; ++c) {
+            const float4 a = *reinterpret_cast<const float4 *>(&sm[0][r][4 * q + 4 * c]);
+            const float4 b = *reinterpret_cast<const float4 *>(&sm[1][r][4 * q + 4 * c]);
+            const float4 d = *reinterpret_cast<const float4 *>(&sm[2][r][4 * q + 4 * c]);
+            w0[4 * c] = a.x; w0[4 * c + 1] = a.y; w0[4 * c + 2] = a.z; w0[4 * c + 3] = a.w;
+            w1[4 * c] = b.x; w1[4 * c + 1] = b.y; w1[4 * c + 2] = b.z; w1[4 * c + 3] = b.w;
+            w2[4 * c] = d.x; w2[4 * c + 1] = d.y; w2[4 * c + 2] = d.z; w2[4 * c + 3] = d.w;
+        }
+        float o0[4], o1[4], o2[4], o3[4], o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = e + N;
+            float b1 = T.g[0] * w0[c], b3 = T.g[0] * w1[c], b5 = T.g[0] * w2[c];
+            float b2 = 0.f, b4 = 0.f, b6 = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                b1 += (w0[c + k] + w0[c - k]) * T.g[k];
+                b4 += (w0[c + k] + w0[c - k]) * T.xxg[k];
+                b2 += (w0[c + k] - w0[c - k]) * T.xg[k];
+                b3 += (w1[c + k] + w1[c - k]) * T.g[k];
+                b6 += (w1[c + k] - w1[c - k]) * T.xg[k];
+                b5 += (w2[c + k] + w2[c - k]) * T.g[k];
+            }
+            o0[e] = b3 * T.ig11;
+            o1[e] = b2 * T.ig11;
+            o2[e] = b1 * T.ig03 + b5 * T.ig33;
+            o3[e] = b1 * T.ig03 + b4 * T.ig33;
+            o4[e] = b6 * T.ig55;
+        }
+        if (x + 3 < cols) {
+            *reinterpret_cast<float4 *>(&dst.at(0, y, x)) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+            *reinterpret_cast<float4 *>(&dst.at(1, y, x)) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            *reinterpret_cast<float4 *>(&dst.at(2, y, x)) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+            *reinterpret_cast<float4 *>(&dst.at(3, y, x)) = make_float4(o3[0], o3[1], o3[2], o3[3]);
+            *reinterpret_cast<float4 *>(&dst.at(4, y, x)) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+            for (int e = 0; e < 4 && x + e < cols; ++e) {
+                dst.at(0, y, x + e) = o0[e];
+                dst.at(1, y, x + e) = o1[e];
+                dst.at(2, y, x + e) = o2[e];
+                dst.at(3, y, x + e) = o3[e];
+                dst.at(4, y, x + e) = o4[e];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // updateMatrices for one pixel (farneback.cu:156-241).
 // ------------------------------------------------------------------------------------------
@@ -1298,13 +1404,19 @@ void FarnebackEngine::solve(Ctx &c) {
         Stack5 R0{L.R[0].p, plane_pitch(w), h}, R1{L.R[1].p, plane_pitch(w), h};
         Stack5 Ma{L.M[0].p, plane_pitch(w), h}, Mb{L.M[1].p, plane_pitch(w), h};
         {
-            const dim3 gp(div_up(w, 32), div_up(h, 8), 2);
+            const dim3 gp(div_up(w, 32), div_up(h, 8), 2), gpf(div_up(w, 64), div_up(h, 32), 2);
             const double bytes = 2.0 * 24.0 * npx;
             Plane a{lv.img[0].p, lv.img[0].pitch}, b{lv.img[1].p, lv.img[1].pitch};
-            if (P.poly_n == 5)
-                B2F_LAUNCH(c, CLS_POLY, bytes, k_farn_polyexp<5>, gp, block, 0, a, b, R0, R1, h, w, L.poly);
-            else
-                B2F_LAUNCH(c, CLS_POLY, bytes, k_farn_polyexp<7>, gp, block, 0, a, b, R0, R1, h, w, L.poly);
+            if (knobs.aux_path == 6) {  // the round-1 kernel (one vertical-pass evaluation per output)
+                if (P.poly_n == 5)
+                    B2F_LAUNCH(c, CLS_POLY, bytes, k_farn_polyexp<5>, gp, block, 0, a, b, R0, R1, h, w, L.poly);
+                else
+                    B2F_LAUNCH(c, CLS_POLY, bytes, k_farn_polyexp<7>, gp, block, 0, a, b, R0, R1, h, w, L.poly);
+            } else if (P.poly_n == 5) {
+                B2F_LAUNCH(c, CLS_POLY, bytes, k_farn_polyexp_fast<5>, gpf, block, 0, a, b, R0, R1, h, w, L.poly);
+            } else {
+                B2F_LAUNCH(c, CLS_POLY, bytes, k_farn_polyexp_fast<7>, gpf, block, 0, a, b, R0, R1, h, w, L.poly);
+            }
         }
 
         // ---- initial matrices, then the fused iterations ----
