@@ -176,7 +176,8 @@ typedef enum b2f_param_id {
                                      in the reference's order), 2 / 3 = separable kernel at 32 / 40 registers; 0, 2
                                      and 3 are bit-identical.  Farneback: fused iteration kernel
                                      at 0 = 128 registers (2 blocks / SM), 3 = 80, 4 = 64 registers, 5 = R1 gather
-                                     with lanes on consecutive pixels (measured slower)                      */
+                                     with lanes on consecutive pixels (measured slower), 6 = round-1 polynomial
+                                     expansion kernel.  All bit-identical.                                   */
 } b2f_param_id;
 
 /* cv::medianBlur for CV_32FC1, ksize 3 or 5, replicated border, not in place: the primitive behind
