@@ -177,7 +177,7 @@ typedef enum b2f_param_id {
                                      and 3 are bit-identical.  Farneback: fused iteration kernel
                                      at 0 = 128 registers (2 blocks / SM), 3 = 80, 4 = 64 registers, 5 = R1 gather
                                      with lanes on consecutive pixels (measured slower), 6 = round-1 polynomial
-                                     expansion kernel.  All bit-identical.                                   */
+                                     expansion and vertical-blur kernels.  All bit-identical.                                   */
 } b2f_param_id;
 
 /* cv::medianBlur for CV_32FC1, ksize 3 or 5, replicated border, not in place: the primitive behind

@@ -195,6 +195,44 @@ __global__ void __launch_bounds__(256) k_farn_blur_v(Plane f0, Plane f1, int row
     (blockIdx.z ? v1 : v0).at(vy, x) = acc;
 }
 
+// Four columns per thread (round 2, the default): the kernel above gives every thread one column and a few taps -- at level 1
+// of a 1080p pair 8 640 live blocks whose threads each wait out two memory round trips for three taps, ~22 us of full SM
+// residency for 25 MB of traffic.  float4 loads / stores cut the blocks by four; rows whose second bilinear tap has weight
+// zero for every y (integral 1 / scale, the default pyrScale = 0.5) are not launched at all (ystep = 2).  Same arithmetic
+// per element: bit-identical.
+__global__ void __launch_bounds__(256) k_farn_blur_v4(Plane f0, Plane f1, int rows, int cols, Plane v0, Plane v1,
+                                                      int lrows, float inv_fy, const float *__restrict__ g,
+                                                      int khalf, int identity, int ystep) {
+    const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);  // rows are padded to 32 floats: x + 3 stays inside the pitch
+    const int vy = blockIdx.y * ystep;  // 0 .. 2*lrows-1
+    if (x >= cols) return;
+    const int y = vy >> 1, t = vy & 1;
+    int sy;
+    if (identity) {
+        if (t) return;
+        sy = y;
+    } else {
+        const float src_y = y * inv_fy;
+        const int y1 = __float2int_rd(src_y);
+        if (t && (src_y - y1) == 0.f) return;  // zero bilinear weight: row never contributes
+        sy = t ? min(y1 + 1, rows - 1) : min(y1, rows - 1);
+    }
+    const Plane src = blockIdx.z ? f1 : f0;
+    const float4 c = __ldg(reinterpret_cast<const float4 *>(&src.at(sy, x)));
+    const float g0 = g[0];
+    float4 acc = make_float4(c.x * g0, c.y * g0, c.z * g0, c.w * g0);
+    for (int j = 1; j <= khalf; ++j) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(&src.at(reflect101(sy - j, rows), x)));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(&src.at(reflect101(sy + j, rows), x)));
+        const float gj = g[j];
+        acc.x += (a.x + b.x) * gj;
+        acc.y += (a.y + b.y) * gj;
+        acc.z += (a.z + b.z) * gj;
+        acc.w += (a.w + b.w) * gj;
+    }
+    *reinterpret_cast<float4 *>(&(blockIdx.z ? v1 : v0).at(vy, x)) = acc;
+}
+
 __device__ __forceinline__ float farn_hblur(const Plane &v, int vy, int sx, int cols, const float *__restrict__ g,
                                             int khalf) {
     float res = v.at(vy, sx) * g[0];
@@ -1393,8 +1431,16 @@ void FarnebackEngine::solve(Ctx &c) {
             const int identity = (h == rows && w == cols) ? 1 : 0;  // resize.cpp:90-94 copy path
             const float inv_fx = inv_scale_from_sizes(cols, w), inv_fy = inv_scale_from_sizes(rows, h);
             const dim3 gv(div_up(cols, 256), 2 * h, 2);
-            B2F_LAUNCH(c, CLS_IMG, 2.0 * 4.0 * ((double)rows * cols + 2.0 * h * cols), k_farn_blur_v, gv, dim3(256), 0,
-                       L.frames[0], L.frames[1], rows, cols, L.vbuf[0], L.vbuf[1], h, inv_fy, taps, kh, identity);
+            if (knobs.aux_path == 6) {  // the round-1 kernel: one column per thread
+                B2F_LAUNCH(c, CLS_IMG, 2.0 * 4.0 * ((double)rows * cols + 2.0 * h * cols), k_farn_blur_v, gv, dim3(256), 0,
+                           L.frames[0], L.frames[1], rows, cols, L.vbuf[0], L.vbuf[1], h, inv_fy, taps, kh, identity);
+            } else {
+                // odd rows of the staging buffer are only read with a non-zero weight when y / fy has a fractional part
+                const int ystep = (identity || inv_fy == std::floor(inv_fy)) ? 2 : 1;
+                const dim3 gv4(div_up(cols, 1024), ystep == 2 ? h : 2 * h, 2);
+                B2F_LAUNCH(c, CLS_IMG, 2.0 * 4.0 * ((double)rows * cols + 2.0 * h * cols), k_farn_blur_v4, gv4, dim3(256), 0,
+                           L.frames[0], L.frames[1], rows, cols, L.vbuf[0], L.vbuf[1], h, inv_fy, taps, kh, identity, ystep);
+            }
             const dim3 gh(div_up(w, 32), div_up(h, 8), 2);
             B2F_LAUNCH(c, CLS_IMG, 2.0 * 4.0 * (2.0 * h * cols + npx), k_farn_blur_h_resize, gh, block, 0, L.vbuf[0],
                        L.vbuf[1], rows, cols, lv.img[0], lv.img[1], h, w, inv_fx, inv_fy, taps, kh, identity);

@@ -170,17 +170,20 @@ def test_iteration_kernel_register_variants_bit_identical(cuda_device):
 @pytest.mark.parametrize("h,w", [(270, 480), (203, 277)])
 @pytest.mark.parametrize("poly_n,sigma", [(5, 1.1), (7, 1.5)])
 def test_polyexp_register_blocked_kernel_bit_identical(cuda_device, h, w, poly_n, sigma):
-    """The default polynomial expansion (64x32 blocks, vertical pass from a register window, float4 horizontal pass) against
-    the round-1 kernel (aux_path 6: one vertical evaluation per output): same expressions in the same order -> same flow bits,
-    including ragged right / bottom blocks and levels smaller than one block."""
+    """The default secondary kernels -- polynomial expansion on 64x32 blocks (vertical pass from a register window, float4
+    horizontal pass) and the sparse vertical blur with four columns per thread -- against the round-1 kernels (aux_path 6):
+    same expressions in the same order -> same flow bits, including ragged right / bottom blocks, levels smaller than one
+    block, and non-integral pyramid scales."""
     import torch
     import opencv_contrib_b200 as ocb
     I0, I1, _ = synth.make_pair(h, w, seed=17, kind="smooth")
     d0, d1 = torch.from_numpy(I0).to(cuda_device), torch.from_numpy(I1).to(cuda_device)
-    outs = []
-    for aux in (0, 6):
-        alg = ocb.FarnebackOpticalFlow_create(polyN=poly_n, polySigma=sigma)
-        alg.setEngineOption("aux_path", aux)
-        outs.append(alg.calc(d0, d1).cpu().numpy())
-    assert np.isfinite(outs[0]).all()
-    assert np.array_equal(outs[0], outs[1]), float(np.abs(outs[0] - outs[1]).max())
+    # pyrScale 0.5: integral 1 / scale (only the even rows of the sparse vertical blur are launched); 0.8: both bilinear rows
+    for pyr_scale, levels in ((0.5, 5), (0.8, 4)):
+        outs = []
+        for aux in (0, 6):
+            alg = ocb.FarnebackOpticalFlow_create(numLevels=levels, pyrScale=pyr_scale, polyN=poly_n, polySigma=sigma)
+            alg.setEngineOption("aux_path", aux)
+            outs.append(alg.calc(d0, d1).cpu().numpy())
+        assert np.isfinite(outs[0]).all()
+        assert np.array_equal(outs[0], outs[1]), (pyr_scale, float(np.abs(outs[0] - outs[1]).max()))
